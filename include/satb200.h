@@ -1,0 +1,203 @@
+/*
+ * satb200.h -- C ABI of libsatb200.so: the B200 (sm_100a) implementation of the batched satellite
+ * environment step of qiaobeibei/PPO-RL-Satellite.
+ *
+ * The reference has no FFI boundary (it is in-process Python); this header is the boundary the
+ * drop-in defines (SURVEY.md s8b tier 2). Each entry point cites the reference interface it
+ * replaces (file:line relative to the upstream repository). The Python facade in
+ * ppo-rl-satellite_b200/ binds these symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *     the library never allocates on behalf of the caller and keeps no global state
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *     *_host entry points copy in, run, copy out and synchronise the stream before returning
+ *   - return value: 0 ok; <0 argument error (SAT_ERR_*); >0 the cudaError_t of the launch
+ *   - SoA columns are 16-byte aligned and `ld` (column stride, in elements) is a multiple of 2
+ *   - thread-safe and re-entrant; one CUDA context per process/GPU is the expected use
+ */
+#ifndef SATB200_H
+#define SATB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SATB200_ABI_VERSION 1
+
+#define SAT_OK          0
+#define SAT_ERR_NULL   -1   /* required pointer is NULL */
+#define SAT_ERR_SIZE   -2   /* bad size / stride / alignment */
+#define SAT_ERR_MODE   -3   /* bad enum value */
+
+int         sat_abi_version(void);
+const char* sat_strerror(int code);          /* static strings; >0 codes map to cudaGetErrorString */
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  RK4 two-body(+J2) propagator.
+ * Replaces StateEq + RungeKutta ("轨道外推-龙格库塔算法.py":15-40) applied `substeps` times with step h
+ * to n independent states. x is SoA [6][ld]: rows x,y,z,vx,vy,vz. j2 = 0 gives pure two-body.
+ * Units are the caller's (km: mu=398600, re=6378.137; m: mu=3.986e14, re=6378137).
+ * ------------------------------------------------------------------------------------------------ */
+int sat_rk4_propagate(double* x, int64_t n, int64_t ld, double h, int substeps,
+                      double mu, double re, double j2, void* stream);
+/* host-buffer form: x_host is [6][n] in pageable or pinned host memory; d_scratch is a device
+ * buffer of 6*ld doubles provided by the caller (ld >= n, even). */
+int sat_rk4_propagate_host(double* x_host, int64_t n, double* d_scratch, int64_t ld, double h,
+                           int substeps, double mu, double re, double j2, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  fused environment step.
+ * Replaces satellites.reset / satellites.step (environment.py:66-79, 81-255) for n independent envs,
+ * including Clohessy_Wiltshire.State_transition_matrix (satellite_function.py:753-781),
+ * calculate_number_hanger_area (environment.py:317-332 -> satellite_function.py:18-99,161-255,
+ * 317-373,462-565 incl. scipy fsolve) and reward_of_action1-4 (environment.py:346-396).
+ * ------------------------------------------------------------------------------------------------ */
+enum { SAT_COL_P = 0, SAT_COL_PV = 3, SAT_COL_E = 6, SAT_COL_EV = 9,
+       SAT_COL_FUEL_C = 12, SAT_COL_FUEL_T = 13, SAT_COL_DIS = 14, SAT_COL_RET = 15, SAT_STATE_COLS = 16 };
+enum { SAT_ICOL_DZ = 0, SAT_ICOL_COUNT = 1, SAT_ICOL_INTSTATE = 2, SAT_ICOL_ERR = 3, SAT_ISTATE_COLS = 4 };
+
+typedef struct {
+    double*  state;    /* [SAT_STATE_COLS][ld] fp64: P(3) Pv(3) E(3) Ev(3) fuel_c fuel_t dis R(discounted return) */
+    int32_t* istate;   /* [SAT_ISTATE_COLS][ld]: dangerous_zone, episode step count, int_state (Q1), err */
+    int64_t  n;        /* number of environments */
+    int64_t  ld;       /* column stride (elements), >= n, even */
+} SatEnvState;
+
+enum { SAT_MODE_CW = 0, SAT_MODE_RK4 = 1 };
+enum { SAT_ACT_F32 = 0, SAT_ACT_F64 = 1 };
+
+typedef struct {
+    int32_t mode;               /* SAT_MODE_CW: the shipped env (CW STM); SAT_MODE_RK4: S RK4 substeps (inertial) */
+    int32_t flag;               /* 0 pursuer training (environment.py:83-179), 1 evader training (:181-255) */
+    int32_t max_episode_steps;  /* environment.py:46 */
+    int32_t auto_reset;         /* 1: envs that finish are reset in the same launch (batched contract) */
+    int32_t action_dtype;       /* SAT_ACT_F32 / SAT_ACT_F64; layout [n][3] */
+    int32_t substeps;           /* rk4 mode: RK4 substeps per env step */
+    int32_t skip_danger_zone;   /* 1: do not evaluate the danger-zone count (keeps it at its stale value) */
+    int32_t reserved;
+    double  d_capture, d_range; /* environment.py:35,45 */
+    double  gamma;              /* reward-scaling discount (normalization.py:57) */
+    double  stm[36];            /* cw mode: row-major 6x6 STM for one step (satellite_function.py:766-773) */
+    double  h, mu, re, j2;      /* rk4 mode: substep size and gravity constants (metres) */
+    double  r_cw[3], v_cw[3];   /* relative->inertial translation (environment.py:338-339) */
+    double  u_grav;             /* danger-zone gravitational parameter (satellite_function.py:28) */
+    double  reset_p[3], reset_e[3]; /* reset() initial positions (environment.py:67,70); velocities are 0 */
+} SatEnvParams;
+
+/* running statistics block (RunningMeanStd, normalization.py:7-29), device resident:
+ * [0] = n, [1..dim] = mean, [1+dim..2dim] = S, [1+2dim..3dim] = std  -> 1 + 3*dim doubles */
+#define SAT_STATS_DOUBLES(dim) (1 + 3 * (dim))
+
+/* bytes of caller-provided workspace sat_env_step / sat_norm_update need for n rows */
+int64_t sat_workspace_bytes(int64_t n);
+
+void sat_env_default_params(SatEnvParams* p);     /* reference literals; cw STM left zero */
+
+/* constructor state (environment.py:41-44: fuel 320/320, dis=inf, dangerous_zone=0) followed by reset() */
+int sat_env_init(const SatEnvState* st, double fuel_c, double fuel_t, const SatEnvParams* p, void* stream);
+/* reset(Flag) (environment.py:66-79) for envs whose mask byte is non-zero (mask NULL = all).
+ * fuel / dis / dangerous_zone persist exactly as in the reference (they are never reset there). */
+int sat_env_reset(const SatEnvState* st, const uint8_t* mask, const SatEnvParams* p, void* stream);
+/* observation of the current state: [n][18] = [P-E, Pv-Ev, P, Pv, E, Ev] (environment.py:76-77) */
+int sat_env_observe(const SatEnvState* st, float* obs_f32, double* obs_f64, void* stream);
+
+/* one step() for all envs.
+ *   pa, ea          [n][3] pursuer / escaper actions (dtype per params)
+ *   count_override  nullable [n]: the `epsiode_count` argument of step(); NULL = internal counter + 1
+ *   obs_f32/obs_f64 nullable [n][18]: next observation (after auto-reset when enabled)
+ *   term_obs_f64    nullable [n][18]: observation before auto-reset (the reference's returned s_)
+ *   reward [n] fp64, done [n] u8: as returned by the reference
+ *   obs_stats / ret_stats  nullable running statistics (dim 18 / dim 1) updated with this step's
+ *                   observations / discounted returns (Normalization, RewardScaling); ret_std_out
+ *                   nullable scalar that receives std(R) after the update
+ *   workspace       sat_workspace_bytes(n) bytes, only needed when a stats pointer is given */
+int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const int32_t* count_override,
+                 float* obs_f32, double* obs_f64, double* term_obs_f64, double* reward, uint8_t* done,
+                 double* obs_stats, double* ret_stats, double* ret_std_out, void* workspace,
+                 const SatEnvParams* p, void* stream);
+
+/* host-buffer form of step(): actions from host memory, obs_f32/reward/done to host memory.
+ * d_io is a caller-provided device staging buffer of sat_env_step_host_bytes(n) bytes. */
+int64_t sat_env_step_host_bytes(int64_t n);
+int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* ea_host,
+                      float* obs_host, double* reward_host, uint8_t* done_host, void* d_io,
+                      const SatEnvParams* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation. Replaces RunningMeanStd.update / Normalization.__call__ (normalization.py:19-43)
+ * for a batch x [n][dim] fp64: merge the batch into stats (Chan; n == 1 is the reference's Welford
+ * step incl. its first-sample rule), then x_out = (x - mean) / (std + 1e-8). update = 0 only normalises.
+ * ------------------------------------------------------------------------------------------------ */
+int sat_norm_update(double* stats, const double* x, int64_t n, int dim, int update,
+                    double* x_out_f64, float* x_out_f32, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  fused Gaussian actor. Replaces PPO_continuous.choose_action -> Actor_Gaussian.get_dist/forward
+ * (ppo_continuous.py:83-95, 176-189) over n observations: mean = max_action*tanh(W3 tanh(W2 tanh(W1 s+b1)+b2)+b3),
+ * a = clamp(mean + exp(log_std)*eps, +-max_action), logp = Normal(mean, std).log_prob(a) per dimension.
+ * eps comes from Philox4x32-10 keyed by (seed, global row id, step) unless eps_in is given.
+ * Only the reference's network shape is supported: in_dim 18, hidden 256, act_dim 3 (SAT_ERR_SIZE otherwise).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float* w1;      /* fc1.weight        [hidden][in_dim]  (torch layout) */
+    const float* b1;      /* fc1.bias          [hidden] */
+    const float* w2;      /* fc2.weight        [hidden][hidden] */
+    const float* b2;      /* fc2.bias          [hidden] */
+    const float* w3;      /* mean_layer.weight [act_dim][hidden] */
+    const float* b3;      /* mean_layer.bias   [act_dim] */
+    const float* log_std; /* [act_dim] (NULL for the critic) */
+    const float* packed;  /* device buffer of SAT_ACTOR_PACKED_FLOATS floats filled by sat_actor_pack() */
+    int32_t in_dim, hidden, act_dim;   /* 18, 256, 3 (critic: act_dim = 1) */
+    int32_t use_tanh;                  /* activation: 1 tanh (args.use_tanh, ppo_continuous.py:74), 0 ReLU */
+    float   max_action;                /* 1.6 */
+} SatActorWeights;
+
+/* kernel-side weight image: W1^T [18][256], b1, W2^T [256][256] (k-major, streamed by TMA bulk copies),
+ * b2, heads [4][256], b3[4], log_std[4]. Re-pack after every optimiser step (one tiny launch). */
+#define SAT_ACTOR_PACKED_FLOATS (18 * 256 + 256 + 256 * 256 + 256 + 4 * 256 + 4 + 4)
+int sat_actor_pack(const SatActorWeights* w, float* packed, void* stream);
+
+/* obs source: either obs_f32 [n][18], or (obs_f32 == NULL) the env state itself, in which case the
+ * observation is rebuilt from the fp64 SoA state and, when obs_stats != NULL, normalised in fp64 with
+ * (x - mean)/(std + 1e-8) before the cast to fp32 (the fused path). obs_out (nullable) receives the
+ * fp32 observation actually fed to the network. row_offset is the global id of row 0 (sharding). */
+int sat_actor_sample(const SatActorWeights* w, const float* obs_f32, const SatEnvState* st,
+                     const double* obs_stats, int64_t n, int64_t row_offset, uint64_t seed, uint64_t step,
+                     const float* eps_in, float* act, float* logp, float* mean_out, float* eps_out,
+                     float* obs_out, void* stream);
+
+/* Critic forward (ppo_continuous.py:123-128): v [n] = fc3(tanh(fc2(tanh(fc1(s))))).
+ * w3/b3 are fc3.weight [1][hidden] / fc3.bias [1]; log_std unused. */
+int sat_critic_forward(const SatActorWeights* w, const float* obs_f32, int64_t n, float* v, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  GAE reverse scan. Replaces the block at ppo_continuous.py:198-210.
+ * time-major form: r, done [T][N]; v [T+1][N] with v[t+1] = V(s') of step t (dw == done);
+ * r_scale nullable [T]: per-step reward scale (1/(std_R+1e-8)) applied on the fly.
+ * flat form: the reference's (B,1) buffers of one env in time order, with separate vs_next and dw.
+ * Outputs adv / v_target share the input layout. sat_adv_normalize applies
+ * (adv - mean)/(std_unbiased + 1e-5) (ppo_continuous.py:210); sums[3] (nullable in/out) lets the caller
+ * all-reduce (sum, sum of squares, count) across ranks between the two phases.
+ * ------------------------------------------------------------------------------------------------ */
+int sat_gae(const float* r, const float* v, const uint8_t* done, const float* r_scale, int64_t T, int64_t N,
+            float gamma, float lamda, float* adv, float* v_target, void* stream);
+int sat_gae_flat(const float* r, const float* vs, const float* vs_next, const float* dw, const float* done,
+                 int64_t B, float gamma, float lamda, float* adv, float* v_target, void* stream);
+int sat_adv_moments(const float* adv, int64_t count, double* sums /*[3] device*/, void* workspace, void* stream);
+int sat_adv_normalize(float* adv, int64_t count, const double* sums /*[3] device*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py): dependent-free DFMA / FFMA chains to measure the FP64 / FP32
+ * vector peaks on the device the bench runs on (MEASURED_PEAKS.json has no such entries).
+ * Each launches one kernel doing `iters` x 16 independent FMAs per thread; flops_out (host) receives
+ * the FLOP count of the launch.
+ * ------------------------------------------------------------------------------------------------ */
+int sat_peak_fp64(double* sink, int blocks, int threads, int iters, double* flops_out_host, void* stream);
+int sat_peak_fp32(float* sink, int blocks, int threads, int iters, double* flops_out_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SATB200_H */

@@ -1,0 +1,326 @@
+// sat_math.cuh -- device math for the satellite environment kernels (sm_100a).
+//
+// Two kinds of arithmetic live here and are deliberately kept apart:
+//   (1) "exact" helpers that reproduce, bit for bit, the IEEE operations the reference's numpy /
+//       OpenBLAS calls perform (ddot, dnrm2-as-sqrt(dot), dgemv, cross, scalar +-*/), written with
+//       explicit __dmul_rn/__dadd_rn/__fma_rn so no compiler flag can re-associate or fuse them;
+//   (2) the RK4 propagator core, written with explicit fma() for minimum FP64-pipe instruction
+//       count (110 per RK4+J2 step), whose parity bar is 1e-9 relative, not bit identity.
+// Translation units that include this file are compiled with -fmad=false, so every fused
+// operation in the binary is one that is spelled fma() here.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define SAT_DEV __device__ __forceinline__
+
+namespace sat {
+
+constexpr double kPi = 3.141592653589793;
+constexpr double kTwoPi = 2 * 3.141592653589793;   // python: 2 * np.pi (exact doubling)
+
+// ------------------------------------------------------------------------------------------
+// (1) exact helpers
+// ------------------------------------------------------------------------------------------
+// np.dot(a3, b3): OpenBLAS ddot tail loop, fma-accumulated left to right
+SAT_DEV double dot3(const double a[3], const double b[3]) {
+    double s = __dmul_rn(a[0], b[0]);
+    s = __fma_rn(a[1], b[1], s);
+    s = __fma_rn(a[2], b[2], s);
+    return s;
+}
+// np.linalg.norm(a3) = sqrt(a.dot(a))
+SAT_DEV double norm3(const double a[3]) { return __dsqrt_rn(dot3(a, a)); }
+
+// np.cross(a, b): products and differences rounded separately
+SAT_DEV void cross3(const double a[3], const double b[3], double c[3]) {
+    c[0] = __dsub_rn(__dmul_rn(a[1], b[2]), __dmul_rn(a[2], b[1]));
+    c[1] = __dsub_rn(__dmul_rn(a[2], b[0]), __dmul_rn(a[0], b[2]));
+    c[2] = __dsub_rn(__dmul_rn(a[0], b[1]), __dmul_rn(a[1], b[0]));
+}
+
+// np.dot(M6x6, x6): OpenBLAS Haswell dgemv_t: 4-lane products, (p0+p2)+(p1+p3), then the 2-element
+// tail as fma(m4, x4, m5*x5)   (satellite_function.py:778-779)
+SAT_DEV double gemv6_row(const double* __restrict__ m, const double x[6]) {
+    double p0 = __dmul_rn(m[0], x[0]), p1 = __dmul_rn(m[1], x[1]);
+    double p2 = __dmul_rn(m[2], x[2]), p3 = __dmul_rn(m[3], x[3]);
+    double head = __dadd_rn(__dadd_rn(p0, p2), __dadd_rn(p1, p3));
+    double tail = __fma_rn(m[4], x[4], __dmul_rn(m[5], x[5]));
+    return __dadd_rn(head, tail);
+}
+
+// cosine between two 3-vectors the way reward_of_action1/2/3/4 compute it (environment.py:351-353):
+// each vector divided by its norm, then np.dot
+SAT_DEV double cosine3(const double a[3], const double b[3]) {
+    double na = norm3(a), nb = norm3(b);
+    double ua[3], ub[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ua[k] = __ddiv_rn(a[k], na); ub[k] = __ddiv_rn(b[k], nb); }
+    return dot3(ua, ub);
+}
+
+// ------------------------------------------------------------------------------------------
+// (2) RK4 two-body + J2 core (script "轨道外推-龙格库塔算法.py":15-40), Nystrom form of classical RK4.
+//     Accelerations are carried divided by -mu; the step constants absorb -mu.
+// ------------------------------------------------------------------------------------------
+struct Rk4Consts {
+    double h;      // h
+    double hh;     // h/2
+    double cx3;    // -mu h^2/4
+    double cx4;    // -mu h^2/2
+    double cx1;    // -mu h^2/6
+    double cv;     // -mu h/6
+    double cj;     // 1.5 J2 Re^2   (0 -> two-body)
+};
+
+SAT_DEV Rk4Consts make_rk4_consts(double h, double mu, double re, double j2) {
+    Rk4Consts c;
+    c.h = h; c.hh = 0.5 * h;
+    c.cx3 = -mu * h * h * 0.25; c.cx4 = -mu * h * h * 0.5; c.cx1 = -mu * h * h / 6.0; c.cv = -mu * h / 6.0;
+    c.cj = 1.5 * j2 * re * re;
+    return c;
+}
+
+// 1/sqrt(x) to ~1 ulp: MUFU.RSQ64H seed (rel. err <= 2^-22.9) + one Halley step (cubic): 5 FP64 ops
+SAT_DEV double rsqrt_halley(double x) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    double yy = y0 * y0;
+    double e = fma(-x, yy, 1.0);
+    double p = fma(0.375, e, 0.5);
+    double pe = p * e;
+    return fma(y0, pe, y0);
+}
+
+// a(x)/(-mu): 20 FP64-pipe instructions with J2, 13 without
+template <bool J2>
+SAT_DEV void accel_scaled(double x, double y, double z, double cj, double& ax, double& ay, double& az) {
+    double zz = z * z;
+    double r2 = fma(x, x, fma(y, y, zz));
+    double ri = rsqrt_halley(r2);
+    double ri2 = ri * ri;
+    double ri3 = ri2 * ri;
+    if (J2) {
+        double c = cj * ri2;            // 1.5 J2 Re^2 / r^2
+        double q = zz * ri2;            // (z/r)^2
+        double t1 = fma(-5.0, q, 1.0);  // 1 - 5 (z/r)^2
+        double fxy = fma(c, t1, 1.0);
+        double fz = fma(2.0, c, fxy);   // 1 + c (3 - 5 (z/r)^2)
+        double kxy = ri3 * fxy, kz = ri3 * fz;
+        ax = kxy * x; ay = kxy * y; az = kz * z;
+    } else {
+        ax = ri3 * x; ay = ri3 * y; az = ri3 * z;
+    }
+}
+
+template <bool J2>
+SAT_DEV void rk4_step(double (&x)[3], double (&v)[3], const Rk4Consts& c) {
+    double a1[3], a2[3], a3[3], a4[3], xa[3], xb[3], xs[3];
+    accel_scaled<J2>(x[0], x[1], x[2], c.cj, a1[0], a1[1], a1[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xa[k] = fma(c.hh, v[k], x[k]);            // x0 + h/2 v0
+    accel_scaled<J2>(xa[0], xa[1], xa[2], c.cj, a2[0], a2[1], a2[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xs[k] = fma(c.cx3, a1[k], xa[k]);         // + h^2/4 a1
+    accel_scaled<J2>(xs[0], xs[1], xs[2], c.cj, a3[0], a3[1], a3[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { xb[k] = fma(c.h, v[k], x[k]); xs[k] = fma(c.cx4, a2[k], xb[k]); }   // x0 + h v0 + h^2/2 a2
+    accel_scaled<J2>(xs[0], xs[1], xs[2], c.cj, a4[0], a4[1], a4[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double t = a2[k] + a3[k];
+        double s3 = a1[k] + t;
+        x[k] = fma(c.cx1, s3, xb[k]);                                      // x0 + h v0 + h^2/6 (a1+a2+a3)
+        double w = (s3 + t) + a4[k];
+        v[k] = fma(c.cv, w, v[k]);                                         // v0 + h/6 (a1+2a2+2a3+a4)
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// orbital elements, satellite_function.py:161-255 (six-element branch; returns false for the
+// circular / parabolic branches, for which the reference's danger-zone code raises)
+// ------------------------------------------------------------------------------------------
+struct Elements { double a, e, i, omega, Omega, f; };
+
+SAT_DEV bool orbital_elements(double miu, const double R0[3], const double V0[3], Elements& el) {
+    double r_norm = norm3(R0), v_norm = norm3(V0);                       // :183-184
+    double r_dot_v = dot3(R0, V0);                                       // :185
+    double v2 = v_norm * v_norm;
+    double energy = 2.0 / r_norm - v2 / miu;                             // :186
+    double c1 = v2 / miu - 1.0 / r_norm, c2 = r_dot_v / miu;             // :193
+    double E[3], H[3], N[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) E[k] = c1 * R0[k] - c2 * V0[k];
+    double e = norm3(E);                                                 // :194
+    cross3(R0, V0, H);                                                   // :197
+    double h = norm3(H);                                                 // :199
+    N[0] = -H[1]; N[1] = H[0]; N[2] = 0.0;                               // :206 cross([0,0,1], H)
+    double n = norm3(N);                                                 // :208
+    if (energy == 0.0 || e == 0.0) return false;
+    el.a = 1.0 / fabs(energy);                                           // :188
+    el.e = e;
+    el.i = acos(H[2] / h);                                               // :210
+    double omega = (n != 0.0) ? acos(dot3(N, E) / n / e) : 0.0;          // :214-217
+    if (E[2] < 0.0) omega = kTwoPi - omega;                              // :221
+    el.omega = omega;
+    double Omega = (n != 0.0) ? acos(N[0] / n) : 0.0;                    // :230-233
+    if (N[1] < 0.0) Omega = kTwoPi - Omega;                              // :237
+    el.Omega = Omega;
+    double f = acos(dot3(E, R0) / e / r_norm);                           // :242
+    if (r_dot_v < 0.0) f = kTwoPi - f;
+    el.f = f;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// scipy.optimize.fsolve(P_fai_equation, alpha_guess): MINPACK hybrd for n = 1 with scipy's defaults
+// (SURVEY.md Appendix B). f(alpha) = A (dvm cos alpha) + sth (-dvm sin alpha), satellite_function.py:559-562.
+// Returns the iterate un-polished, exactly like the reference uses result[0].
+// ------------------------------------------------------------------------------------------
+struct PFai {
+    double A, sth, dvm;
+    SAT_DEV double operator()(double alpha) const {
+        double s, c;
+        sincos(alpha, &s, &c);
+        return A * (dvm * c) + sth * (-dvm * s);
+    }
+};
+
+template <class F>
+__device__ __noinline__ double hybrd1(const F& fcn, double x0) {
+    const double epsmch = 2.220446049250313e-16, xtol = 1.49012e-08, factor = 100.0;
+    const double sqeps = 1.4901161193847656e-08;   // sqrt(epsmch), exact power of two
+    const int maxfev = 400;
+    double x = x0, fv = fcn(x), fnorm = fabs(fv), d = 0.0, delta = 0.0, xnorm = 0.0;
+    int nfev = 1, iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
+    for (;;) {
+        bool jeval = true;
+        double h = sqeps * fabs(x);
+        if (h == 0.0) h = sqeps;
+        double a = (fcn(x + h) - fv) / h; ++nfev;
+        double r = -a, q = (a != 0.0) ? -1.0 : 1.0;
+        if (iter == 1) {
+            d = (fabs(a) != 0.0) ? fabs(a) : 1.0;
+            xnorm = fabs(d * x);
+            delta = factor * xnorm;
+            if (delta == 0.0) delta = factor;
+        }
+        double qtf = q * fv;
+        d = fmax(d, fabs(a));
+        for (;;) {
+            double t = r;
+            if (t == 0.0) { t = epsmch * fabs(r); if (t == 0.0) t = epsmch; }
+            double xgn = qtf / t, qnorm = fabs(d * xgn), step;
+            if (qnorm <= delta) step = xgn;
+            else {
+                double w = (r * qtf) / d, gnorm = fabs(w), sgnorm = 0.0, alpha = delta / qnorm;
+                if (gnorm != 0.0) {
+                    w = (w / gnorm) / d;
+                    double tt = fabs(r * w);
+                    sgnorm = (gnorm / tt) / tt; alpha = 0.0;
+                    if (sgnorm < delta) {
+                        double bnorm = fabs(qtf), dq = delta / qnorm, sd = sgnorm / delta;
+                        double tmp = (bnorm / gnorm) * (bnorm / qnorm) * sd;
+                        tmp = tmp - dq * sd * sd + sqrt((tmp - dq) * (tmp - dq) + (1.0 - dq * dq) * (1.0 - sd * sd));
+                        alpha = (dq * (1.0 - sd * sd)) / tmp;
+                    }
+                }
+                step = (1.0 - alpha) * fmin(sgnorm, delta) * w + alpha * xgn;
+            }
+            double p = -step, xt = x + p, pnorm = fabs(d * p);
+            if (iter == 1) delta = fmin(delta, pnorm);
+            double ft = fcn(xt); ++nfev;
+            double fnorm1 = fabs(ft);
+            double actred = (fnorm1 < fnorm) ? 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm) : -1.0;
+            double pred = qtf + r * p;
+            double prered = (fabs(pred) < fnorm) ? 1.0 - (fabs(pred) / fnorm) * (fabs(pred) / fnorm) : 0.0;
+            double ratio = (prered > 0.0) ? actred / prered : 0.0;
+            if (ratio < 0.1) { ncsuc = 0; ++ncfail; delta = 0.5 * delta; }
+            else {
+                ncfail = 0; ++ncsuc;
+                if (ratio >= 0.5 || ncsuc > 1) delta = fmax(delta, pnorm / 0.5);
+                if (fabs(ratio - 1.0) <= 0.1) delta = pnorm / 0.5;
+            }
+            if (ratio >= 1e-4) { x = xt; fv = ft; xnorm = fabs(d * x); fnorm = fnorm1; ++iter; }
+            ++nslow1; if (actred >= 1e-3) nslow1 = 0;
+            if (jeval) ++nslow2;
+            if (actred >= 0.1) nslow2 = 0;
+            if (delta <= xtol * xnorm || fnorm == 0.0) return x;               // info 1
+            if (nfev >= maxfev) return x;                                      // info 2
+            if (0.1 * fmax(0.1 * delta, pnorm) <= epsmch * xnorm) return x;    // info 3
+            if (nslow2 == 5 || nslow1 == 10) return x;                         // info 4 / 5
+            if (ncfail == 2) break;
+            double s = q * ft, v = (s - pred) / pnorm, uu = d * ((d * p) / pnorm);
+            if (ratio >= 1e-4) qtf = s;
+            r = r + uu * v; jeval = false;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// rf_extreme_point('orbit_c1' / 'orbit_c2'), satellite_function.py:462-556, with fai = 0 (:33).
+// f_cx is f_c1 or f_c2. Writes (rf_max, rf_min).
+// ------------------------------------------------------------------------------------------
+struct PursuerOrbit { double u, dv, e_c, f0_c, r_c, p_c; };
+
+SAT_DEV double rf_from_alpha(const PursuerOrbit& o, double sq_e_sin, double sq_k, double dvm, double alpha,
+                             double cth, double sth) {
+    double s, c;
+    sincos(alpha, &s, &c);
+    double v1x = sq_e_sin + dvm * c;                                      // :525 / :541
+    double v1y = sq_k + dvm * s;                                          // :526 / :542 (cos(beta) = 1 folded by caller)
+    double hm = o.r_c * v1y;
+    return (hm * hm) / (o.u * (1.0 - cth) + hm * v1y * cth - hm * v1x * sth);   // :530 / :545
+}
+
+static __device__ __noinline__ void rf_extreme_point(const PursuerOrbit& o, double f_cx, double& rf_max, double& rf_min) {
+    double df = f_cx - o.f0_c;
+    double sdf, cdf;
+    sincos(df, &sdf, &cdf);
+    double k = 1.0 + o.e_c * cos(o.f0_c);
+    double temp1 = (sdf * sdf) / (o.u * (k * k) / (o.p_c * (o.dv * o.dv)) - 1.0);     // :466 / :481
+    if (!(0.0 <= temp1)) { rf_max = 0.0; rf_min = 0.0; return; }                      // :478
+    double beta = atan(0.0 / sdf);                                                    // :469, tan(fai) = 0
+    double sb = sin(beta), cb = cos(beta);
+    double dvm = sqrt(o.dv * o.dv - o.u * (k * k) * (sb * sb) / o.p_c);               // :470
+    double theta = 0.0;                                                               // :464 (stays 0 outside both ranges, Q5)
+    if ((-kTwoPi <= df && df < -kPi) || (0.0 <= df && df < kPi)) theta = acos(cdf * 1.0);             // :473-474
+    else if ((-kPi <= df && df < 0.0) || (kPi <= df && df < kTwoPi)) theta = kTwoPi - acos(cdf * 1.0);  // :475-476
+    double sth, cth;
+    sincos(theta, &sth, &cth);
+    double sq = sqrt(o.u / o.p_c);
+    double sq_e_sin = sq * o.e_c * sin(o.f0_c);                                       // :518 first term
+    double sq_k = sq * (1.0 + o.e_c * cos(o.f0_c)) * cb;                              // :519 first term
+    double r[2];
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+        double ag = (j == 0) ? kPi / 2 : -kPi / 2;                                    // :516 / :534
+        double sg, cg;
+        sincos(ag, &sg, &cg);
+        double v1x = sq_e_sin + dvm * cg;
+        double v1y = sq_k + dvm * sg;
+        double h = o.r_c * v1y;                                                       // :521
+        PFai f;
+        f.A = (2.0 * o.u * (1.0 - cth)) / (h * v1y) - v1x * sth / v1y;                // :560
+        f.sth = sth; f.dvm = dvm;
+        double alpha = hybrd1(f, ag);                                                 // :523 / :540
+        r[j] = fabs(rf_from_alpha(o, sq_e_sin, sq_k, dvm, alpha, cth, sth));          // :549-550
+    }
+    if (r[0] < r[1]) { rf_max = r[1]; rf_min = r[0]; } else { rf_max = r[0]; rf_min = r[1]; }   // :551-554
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter = (row_lo, row_hi, step_lo, step_hi), key = seed
+// ------------------------------------------------------------------------------------------
+SAT_DEV void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+}  // namespace sat

@@ -1,0 +1,421 @@
+"""Host-side engine: device-resident environment batch, actor sampler, GAE and RK4 entry points.
+
+Everything here is plumbing around libsatb200.so (include/satb200.h): torch allocates device memory
+and provides the stream; all arithmetic of the hot path runs in the CUDA kernels. There is no CPU
+fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+# physical constants of the reference
+MU_KM, RE_KM, J2 = 398600.0, 6378.137, 0.00108263          # RK4 script :9-11
+MU_M, RE_M = 3.986e14, 6378137.0                           # satellite_function.py:28
+OBS_DIM, ACT_DIM = 18, 3
+
+
+def cw_stm(t: float = 100.0) -> np.ndarray:
+    """6x6 Clohessy-Wiltshire state-transition matrix exactly as the reference builds it
+    (satellite_function.py:753-773): python-float omega/tau, numpy sin/cos."""
+    u = 3.986e14
+    R = 42164000
+    omega = math.sqrt(u / (R ** 3))
+    tau = omega * t
+    s = np.sin(tau)
+    c = np.cos(tau)
+    return np.array([
+        [4 - 3 * c, 0, 0, s / omega, 2 * (1 - c) / omega, 0],
+        [6 * (s - tau), 1, 0, -2 * (1 - c) / omega, 4 * s / omega - 3 * tau, 0],
+        [0, 0, c, 0, 0, s / omega],
+        [3 * omega * s, 0, 0, c, 2 * s, 0],
+        [6 * omega * (c - 1), 0, 0, -2 * s, 4 * c - 3, 0],
+        [0, 0, -omega * s, 0, 0, c]], dtype=np.float64)
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------------------------- K1
+def rk4_propagate(x, h: float, substeps: int, mu: float = MU_KM, re: float = RE_KM, j2: float = J2):
+    """In-place RK4 propagation of a CUDA fp64 tensor x [6, N] (rows x,y,z,vx,vy,vz).
+    Replaces `substeps` calls of RungeKutta (RK4 script :34-40) per state."""
+    torch = L.require_cuda()
+    if x.dtype != torch.float64 or x.dim() != 2 or x.shape[0] != 6:
+        raise L.SatError("x must be a float64 CUDA tensor of shape [6, N]")
+    n, ld = x.shape[1], x.stride(0)
+    if x.stride(1) != 1:
+        raise L.SatError("x rows must be contiguous")
+    L.check(L.load().sat_rk4_propagate(x.data_ptr(), n, ld, float(h), int(substeps), float(mu), float(re),
+                                       float(j2), L.stream_ptr()), "sat_rk4_propagate")
+    return x
+
+
+def alloc_soa(rows: int, n: int, dtype, device):
+    """[rows, n] view of a buffer whose row stride is even and 16-byte aligned (vector loads)."""
+    torch = L.require_cuda()
+    ld = _round_up(n, 2)
+    buf = torch.zeros((rows, ld), dtype=dtype, device=device)
+    return buf[:, :n], buf
+
+
+class Rk4HostPropagator:
+    """Host-buffer form (numpy in / numpy out through pinned staging): the e2e path of K1."""
+
+    def __init__(self, n: int, device="cuda"):
+        torch = L.require_cuda()
+        self.n = n
+        self.ld = _round_up(n, 2)
+        self.dev = torch.empty((6, self.ld), dtype=torch.float64, device=device)
+        self.pinned = torch.empty((6, n), dtype=torch.float64).pin_memory()
+
+    def __call__(self, x_np: np.ndarray, h, substeps, mu=MU_KM, re=RE_KM, j2=J2) -> np.ndarray:
+        self.pinned.numpy()[...] = x_np
+        L.check(L.load().sat_rk4_propagate_host(self.pinned.data_ptr(), self.n, self.dev.data_ptr(), self.ld,
+                                                float(h), int(substeps), float(mu), float(re), float(j2),
+                                                L.stream_ptr()), "sat_rk4_propagate_host")
+        return self.pinned.numpy().copy()
+
+
+# --------------------------------------------------------------------------------------------- stats
+class RunningStats:
+    """Device-resident RunningMeanStd (normalization.py:7-29): [n | mean[dim] | S[dim] | std[dim]]."""
+
+    def __init__(self, dim: int, device="cuda"):
+        torch = L.require_cuda()
+        self.dim = dim
+        self.buf = torch.zeros(1 + 3 * dim, dtype=torch.float64, device=device)
+
+    @property
+    def n(self):
+        return int(self.buf[0].item())
+
+    @property
+    def mean(self):
+        return self.buf[1:1 + self.dim]
+
+    @property
+    def S(self):
+        return self.buf[1 + self.dim:1 + 2 * self.dim]
+
+    @property
+    def std(self):
+        return self.buf[1 + 2 * self.dim:1 + 3 * self.dim]
+
+    def update_normalize(self, x, update=True, out_dtype=None):
+        """x: CUDA fp64 [n, dim]. Merges the batch (update=True) then returns (x-mean)/(std+1e-8)."""
+        torch = L.require_cuda()
+        x = x.contiguous()
+        n = x.shape[0]
+        ws = torch.empty(L.load().sat_workspace_bytes(n), dtype=torch.uint8, device=x.device)
+        out64 = torch.empty_like(x) if out_dtype in (None, torch.float64) else None
+        out32 = torch.empty(x.shape, dtype=torch.float32, device=x.device) if out_dtype == torch.float32 else None
+        L.check(L.load().sat_norm_update(self.buf.data_ptr(), x.data_ptr(), n, self.dim, int(bool(update)),
+                                         L.ptr(out64), L.ptr(out32), ws.data_ptr(), L.stream_ptr()),
+                "sat_norm_update")
+        return out64 if out64 is not None else out32
+
+
+# --------------------------------------------------------------------------------------------- K2
+class EnvBatch:
+    """N independent `satellites` environments resident on one GPU (SoA fp64 state, int32 counters).
+
+    mode "cw": the env as shipped (CW STM, environment.py:117-121) -> bit-level parity target.
+    mode "rk4": propagation by `substeps` RK4 steps of size h of the inertial two-body+J2 ODE
+    (north-star production path; relative<->inertial by the reference's translation, environment.py:334-343).
+    """
+
+    def __init__(self, n: int, mode: str = "cw", flag: int = 0, d_capture: float = 100000.0,
+                 d_range: float = 100000.0, fuel_c: float = 320.0, fuel_t: float = 320.0,
+                 max_episode_steps: int = 1000, auto_reset: bool = True, substeps: int = 100, h: float = 1.0,
+                 j2: float = J2, gamma: float = 0.99, skip_danger_zone: bool = False, t_step: float = 100.0,
+                 stm: np.ndarray | None = None, device="cuda"):
+        torch = L.require_cuda()
+        self.torch = torch
+        self.lib = L.load()
+        self.n = int(n)
+        self.device = torch.device(device)
+        self.state, self._state_buf = alloc_soa(L.SAT_STATE_COLS, self.n, torch.float64, self.device)
+        self.istate, self._istate_buf = alloc_soa(L.SAT_ISTATE_COLS, self.n, torch.int32, self.device)
+        self.ld = self._state_buf.shape[1]
+        self.st = L.SatEnvState(self._state_buf.data_ptr(), self._istate_buf.data_ptr(), self.n, self.ld)
+        p = L.default_params()
+        p.mode = {"cw": L.MODE_CW, "rk4": L.MODE_RK4}[mode]
+        p.flag = int(flag)
+        p.max_episode_steps = int(max_episode_steps)
+        p.auto_reset = int(bool(auto_reset))
+        p.substeps = int(substeps)
+        p.skip_danger_zone = int(bool(skip_danger_zone))
+        p.d_capture, p.d_range, p.gamma = float(d_capture), float(d_range), float(gamma)
+        p.h, p.j2 = float(h), float(j2)
+        M = cw_stm(t_step) if stm is None else np.asarray(stm, dtype=np.float64)
+        for i, v in enumerate(M.ravel()):
+            p.stm[i] = float(v)
+        self.params = p
+        self.mode = mode
+        self._fuel0 = (float(fuel_c), float(fuel_t))
+        self.workspace = torch.empty(self.lib.sat_workspace_bytes(self.n), dtype=torch.uint8, device=self.device)
+        self.reward = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        self.done = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        self._host = None
+        self.init()
+
+    # -- parameters that the reference lets the driver patch after construction (CPPO_main.py:98)
+    @property
+    def d_capture(self):
+        return self.params.d_capture
+
+    @d_capture.setter
+    def d_capture(self, v):
+        self.params.d_capture = float(v)
+
+    def init(self):
+        """constructor state + reset() (environment.py:26-62, 66-79)."""
+        L.check(self.lib.sat_env_init(C.byref(self.st), self._fuel0[0], self._fuel0[1], C.byref(self.params),
+                                      L.stream_ptr()), "sat_env_init")
+
+    def reset(self, mask=None, flag=None):
+        """reset(Flag) for the masked envs (uint8 CUDA tensor) or all; fuel/dis/dangerous_zone persist (Q2)."""
+        if flag is not None:
+            self.params.flag = int(flag)
+        L.check(self.lib.sat_env_reset(C.byref(self.st), L.ptr(mask), C.byref(self.params), L.stream_ptr()),
+                "sat_env_reset")
+
+    def observe(self, dtype=None):
+        torch = self.torch
+        dtype = dtype or torch.float64
+        out = torch.empty((self.n, OBS_DIM), dtype=dtype, device=self.device)
+        L.check(self.lib.sat_env_observe(C.byref(self.st), L.ptr(out) if dtype == torch.float32 else None,
+                                         L.ptr(out) if dtype == torch.float64 else None, L.stream_ptr()),
+                "sat_env_observe")
+        return out
+
+    def step(self, pa, ea, count=None, obs_f32=None, obs_f64=None, term_obs_f64=None, reward=None, done=None,
+             obs_stats: RunningStats | None = None, ret_stats: RunningStats | None = None, ret_std_out=None):
+        """One step() of every env. pa/ea: CUDA [n,3] float32 or float64. Outputs are written into the
+        given tensors (allocated by the caller to keep the hot loop allocation-free)."""
+        torch = self.torch
+        if pa.dtype != ea.dtype or pa.dtype not in (torch.float32, torch.float64):
+            raise L.SatError("actions must both be float32 or both float64")
+        self.params.action_dtype = L.ACT_F32 if pa.dtype == torch.float32 else L.ACT_F64
+        reward = self.reward if reward is None else reward
+        done = self.done if done is None else done
+        L.check(self.lib.sat_env_step(C.byref(self.st), L.ptr(pa), L.ptr(ea), L.ptr(count), L.ptr(obs_f32),
+                                      L.ptr(obs_f64), L.ptr(term_obs_f64), L.ptr(reward), L.ptr(done),
+                                      L.ptr(obs_stats.buf) if obs_stats is not None else None,
+                                      L.ptr(ret_stats.buf) if ret_stats is not None else None,
+                                      L.ptr(ret_std_out), self.workspace.data_ptr(), C.byref(self.params),
+                                      L.stream_ptr()), "sat_env_step")
+        return reward, done
+
+    # -- host-buffer form: the reference-facing call with numpy in / numpy out (e2e path)
+    def step_host(self, pa_np: np.ndarray, ea_np: np.ndarray):
+        torch = self.torch
+        if self._host is None:
+            n = self.n
+            self._host = dict(
+                pa=torch.empty((n, 3), dtype=torch.float32).pin_memory(),
+                ea=torch.empty((n, 3), dtype=torch.float32).pin_memory(),
+                obs=torch.empty((n, OBS_DIM), dtype=torch.float32).pin_memory(),
+                rew=torch.empty(n, dtype=torch.float64).pin_memory(),
+                done=torch.empty(n, dtype=torch.uint8).pin_memory(),
+                dio=torch.empty(self.lib.sat_env_step_host_bytes(n), dtype=torch.uint8, device=self.device))
+        hb = self._host
+        hb["pa"].numpy()[...] = pa_np
+        hb["ea"].numpy()[...] = ea_np
+        L.check(self.lib.sat_env_step_host(C.byref(self.st), hb["pa"].data_ptr(), hb["ea"].data_ptr(),
+                                           hb["obs"].data_ptr(), hb["rew"].data_ptr(), hb["done"].data_ptr(),
+                                           hb["dio"].data_ptr(), C.byref(self.params), L.stream_ptr()),
+                "sat_env_step_host")
+        return hb["obs"].numpy(), hb["rew"].numpy(), hb["done"].numpy()
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self.n * 3 * 4 * 2
+
+    @property
+    def d2h_bytes_per_step(self):
+        return self.n * (OBS_DIM * 4 + 8 + 1)
+
+    # -- convenient views (fp64, exact)
+    def positions(self):
+        s = self.state
+        return s[0:3].T, s[3:6].T, s[6:9].T, s[9:12].T
+
+    def set_state(self, P, Pv, E, Ev):
+        """overwrite the 12 kinematic columns (tensors/arrays [n,3]); clears the int64 quirk flag."""
+        torch = self.torch
+        for off, a in ((0, P), (3, Pv), (6, E), (9, Ev)):
+            self.state[off:off + 3] = torch.as_tensor(np.asarray(a, dtype=np.float64), device=self.device).T
+        self.istate[L.ICOL_INTSTATE].zero_()
+
+    @property
+    def fuel_c(self):
+        return self.state[L.COL_FUEL_C]
+
+    @property
+    def fuel_t(self):
+        return self.state[L.COL_FUEL_T]
+
+    @property
+    def dis(self):
+        return self.state[L.COL_DIS]
+
+    @property
+    def dangerous_zone(self):
+        return self.istate[L.ICOL_DZ]
+
+    @property
+    def episode_count(self):
+        return self.istate[L.ICOL_COUNT]
+
+    @property
+    def err(self):
+        return self.istate[L.ICOL_ERR]
+
+
+# --------------------------------------------------------------------------------------------- K3
+class GaussianActorKernel:
+    """Fused Actor_Gaussian forward + sampling (ppo_continuous.py:83-95, 176-189) for batches."""
+
+    KEYS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "mean_layer.weight", "mean_layer.bias", "log_std")
+
+    def __init__(self, max_action: float = 1.6, use_tanh: bool = True, device="cuda", critic: bool = False):
+        torch = L.require_cuda()
+        self.torch = torch
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.critic = critic
+        self.packed = torch.zeros(L.ACTOR_PACKED_FLOATS, dtype=torch.float32, device=self.device)
+        self.max_action = float(max_action)
+        self.use_tanh = int(bool(use_tanh))
+        self._keep = None
+        self.w = None
+
+    def load_state_dict(self, sd):
+        """sd: torch state_dict (or dict of arrays) with the reference's parameter names."""
+        torch = self.torch
+        names = (("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc3.weight", "fc3.bias") if self.critic
+                 else self.KEYS[:6])
+        t = [torch.as_tensor(np.asarray(sd[k].detach().cpu() if hasattr(sd[k], "detach") else sd[k]),
+                             dtype=torch.float32).contiguous().to(self.device) for k in names]
+        if self.critic:
+            ls = None
+        else:
+            v = sd["log_std"]
+            ls = torch.as_tensor(np.asarray(v.detach().cpu() if hasattr(v, "detach") else v),
+                                 dtype=torch.float32).reshape(-1).contiguous().to(self.device)
+        hid, in_dim = t[0].shape
+        heads = t[4].shape[0]
+        w = L.SatActorWeights(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(),
+                              t[5].data_ptr(), ls.data_ptr() if ls is not None else None, self.packed.data_ptr(),
+                              in_dim, hid, heads, self.use_tanh, self.max_action)
+        L.check(self.lib.sat_actor_pack(C.byref(w), self.packed.data_ptr(), L.stream_ptr()), "sat_actor_pack")
+        self._keep = (t, ls)
+        self.w = w
+        return self
+
+    def sample(self, obs=None, env: EnvBatch | None = None, obs_stats: RunningStats | None = None, seed: int = 0,
+               step: int = 0, row_offset: int = 0, eps_in=None, act=None, logp=None, mean_out=None, eps_out=None,
+               obs_out=None):
+        """obs: CUDA fp32 [n,18]; or env=EnvBatch to read (and optionally normalise) the state directly."""
+        torch = self.torch
+        if self.w is None:
+            raise L.SatError("weights not loaded")
+        n = obs.shape[0] if obs is not None else env.n
+        act = torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device) if act is None else act
+        logp = torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device) if logp is None else logp
+        L.check(self.lib.sat_actor_sample(C.byref(self.w), L.ptr(obs), C.byref(env.st) if env is not None else None,
+                                          L.ptr(obs_stats.buf) if obs_stats is not None else None, n,
+                                          int(row_offset), int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1),
+                                          L.ptr(eps_in), L.ptr(act), L.ptr(logp), L.ptr(mean_out), L.ptr(eps_out),
+                                          L.ptr(obs_out), L.stream_ptr()), "sat_actor_sample")
+        return act, logp
+
+    def value(self, obs, out=None):
+        torch = self.torch
+        if not self.critic:
+            raise L.SatError("not a critic kernel")
+        n = obs.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=self.device) if out is None else out
+        L.check(self.lib.sat_critic_forward(C.byref(self.w), L.ptr(obs), n, L.ptr(out), L.stream_ptr()),
+                "sat_critic_forward")
+        return out
+
+
+# --------------------------------------------------------------------------------------------- K4
+def gae_time_major(r, v, done, gamma=0.99, lamda=0.95, r_scale=None, adv=None, v_target=None):
+    """r [T,N] fp32, v [T+1,N] fp32, done [T,N] uint8 (CUDA). ppo_continuous.py:198-208 per env column."""
+    torch = L.require_cuda()
+    T, N = r.shape
+    adv = torch.empty_like(r) if adv is None else adv
+    v_target = torch.empty_like(r) if v_target is None else v_target
+    L.check(L.load().sat_gae(L.ptr(r), L.ptr(v), L.ptr(done), L.ptr(r_scale), T, N, float(gamma), float(lamda),
+                             L.ptr(adv), L.ptr(v_target), L.stream_ptr()), "sat_gae")
+    return adv, v_target
+
+
+def gae_flat(r, vs, vs_next, dw, done, gamma=0.99, lamda=0.95):
+    """The reference's (B,1) buffers of one env in time order (all CUDA fp32)."""
+    torch = L.require_cuda()
+    r, vs, vs_next, dw, done = (t.reshape(-1).contiguous() for t in (r, vs, vs_next, dw, done))
+    adv = torch.empty_like(r)
+    vt = torch.empty_like(r)
+    L.check(L.load().sat_gae_flat(L.ptr(r), L.ptr(vs), L.ptr(vs_next), L.ptr(dw), L.ptr(done), r.numel(),
+                                  float(gamma), float(lamda), L.ptr(adv), L.ptr(vt), L.stream_ptr()), "sat_gae_flat")
+    return adv, vt
+
+
+def adv_moments(adv):
+    """(sum, sum of squares, count) of a CUDA fp32 tensor as a 3-element fp64 CUDA tensor."""
+    torch = L.require_cuda()
+    sums = torch.empty(3, dtype=torch.float64, device=adv.device)
+    ws = torch.empty(4096 * 2, dtype=torch.float64, device=adv.device)
+    L.check(L.load().sat_adv_moments(L.ptr(adv.reshape(-1)), adv.numel(), L.ptr(sums), L.ptr(ws), L.stream_ptr()),
+            "sat_adv_moments")
+    return sums
+
+
+def adv_normalize_(adv, sums=None, group=None):
+    """in-place (adv-mean)/(std_unbiased+1e-5) (ppo_continuous.py:210); with `group` the three moments are
+    all-reduced across ranks first, so every rank normalises with the global statistics."""
+    torch = L.require_cuda()
+    if sums is None:
+        sums = adv_moments(adv)
+    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                             and torch.distributed.get_world_size() > 1 and group is not False):
+        torch.distributed.all_reduce(sums, group=group if group not in (None, True) else None)
+    flat = adv.reshape(-1)
+    L.check(L.load().sat_adv_normalize(L.ptr(flat), flat.numel(), L.ptr(sums), L.stream_ptr()), "sat_adv_normalize")
+    return adv
+
+
+# --------------------------------------------------------------------------------------------- peaks
+def measure_vector_peak(dtype="fp64", iters=4096, repeats=5):
+    """TFLOP/s of a dependent-free FMA chain kernel on the current device (roofline denominator)."""
+    torch = L.require_cuda()
+    lib = L.load()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    blocks, threads = sms * 8, 256
+    flops = C.c_double()
+    if dtype == "fp64":
+        sink = torch.zeros(1, dtype=torch.float64, device="cuda")
+        fn = lib.sat_peak_fp64
+    else:
+        sink = torch.zeros(1, dtype=torch.float32, device="cuda")
+        fn = lib.sat_peak_fp32
+    best = 0.0
+    for i in range(repeats + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(fn(sink.data_ptr(), blocks, threads, iters, C.byref(flops), L.stream_ptr()), "sat_peak")
+        e1.record()
+        e1.synchronize()
+        if i >= 2:
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
