@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched satellite environment step on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): RK4 satellite env-steps/sec. A "step" is one pass of the hot path over one
+batch: pursuer actor sample + evader actor sample (fused Gaussian actors, Philox) + one fused env step
+in rk4 mode (impulse, S RK4+J2 substeps of both craft, terminal checks, danger-zone count, reward,
+observation/return running statistics) for every env of the batch.
+
+N = 1 workload: BASELINE config 3 (65 536 envs, S = 100 substeps of h = 1 s, J2 on). N > 1: the same
+per-GPU batch on every rank (weak scaling; envs are independent, no data-path collective).
+
+One JSON line on stdout (rank 0). See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_ENV_STEP = 34800.0        # 2 craft x 100 substeps x 174 FLOP (RK4 + J2), fp64
+FLOP_RK4_J2 = 174.0
+FLOP_ACTOR = 141824.0          # fp32 per actor forward
+BYTES_ENV_STEP = 345.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--substeps", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-envs", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_env_steps_per_s(n_envs, steps, substeps, nthreads):
+    """Times the CPU restatement of the same workload (oracle port of the reference's env logic + the RK4
+    script's integrator) on the host cores: returns env-steps/s."""
+    from oracle import oracle as O
+    env = O.BatchEnv(n_envs, d_capture=20000.0, max_episode_steps=1000, nthreads=nthreads)
+    rng = np.random.default_rng(1)
+    pa = rng.uniform(-2, 2, (n_envs, 3)).astype(np.float32).astype(np.float64)
+    ea = rng.uniform(-2, 2, (n_envs, 3)).astype(np.float32).astype(np.float64)
+    env.step_rk4(pa, ea, substeps=substeps)                      # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        env.step_rk4(pa, ea, substeps=substeps)
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = args.cpu_sample_envs or 64 * cores
+    # size the sample: one probe step, then as many envs as fit ~3 s per timed step
+    rate, _ = cpu_env_steps_per_s(min(n_envs, 8 * cores), 1, args.substeps, cores)
+    n_envs = int(max(cores, min(65536, rate * 3.0)))
+    times = []
+    from oracle import oracle as O
+    env = O.BatchEnv(n_envs, d_capture=20000.0, max_episode_steps=1000, nthreads=cores)
+    rng = np.random.default_rng(1)
+    for i in range(args.warmup + args.steps):
+        pa = rng.uniform(-2, 2, (n_envs, 3)).astype(np.float32).astype(np.float64)
+        ea = rng.uniform(-2, 2, (n_envs, 3)).astype(np.float32).astype(np.float64)
+        t0 = time.perf_counter()
+        env.step_rk4(pa, ea, substeps=args.substeps)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    value = n_envs / (ms * 1e-3)
+    line = {"impl": "reference", "metric": "rk4_env_steps_per_sec", "value": value, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "envs_per_gpu": args.envs, "substeps": args.substeps,
+                       "note": "reference is pure Python and cannot travel to the GPU box; this arm times the CPU oracle "
+                               "port (C, OpenMP, literal restatement incl. MINPACK hybrd) of the same env step"},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_envs} envs x {args.steps} steps (S={args.substeps} RK4+J2 substeps, env step only, actions given)"},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"config3: {args.envs} envs/GPU, full step = 2 fused Gaussian actors (18-256-256-3, Philox) + fused env step "
+            f"in rk4 mode (S={args.substeps} x h=1s RK4 two-body+J2 of both craft, impulse, terminal checks, danger-zone count, "
+            f"reward, running obs/return statistics)")
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def orthogonal_actor_state(torch, seed):
+    """random-init weights of the reference's Actor_Gaussian (orthogonal init, ppo_continuous.py:76-81)."""
+    g = torch.Generator().manual_seed(seed)
+    def orth(rows, cols, gain):
+        w = torch.empty(rows, cols)
+        torch.nn.init.orthogonal_(w, gain=gain, generator=g)
+        return w
+    return {"fc1.weight": orth(256, 18, 1.0), "fc1.bias": torch.zeros(256), "fc2.weight": orth(256, 256, 1.0),
+            "fc2.bias": torch.zeros(256), "mean_layer.weight": orth(3, 256, 0.01), "mean_layer.bias": torch.zeros(3),
+            "log_std": torch.zeros(1, 3)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ppo_rl_satellite_b200 import engine as eng
+    from ppo_rl_satellite_b200 import _lib as L
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n = args.envs
+    S = args.substeps
+
+    env = eng.EnvBatch(n, mode="rk4", substeps=S, h=1.0, d_capture=20000.0, max_episode_steps=1000, auto_reset=True, device=dev)
+    # synthetic random relative orbits around the reset geometry (different per rank / env)
+    rng = np.random.default_rng(1234 + rank)
+    P = np.array([200000.0, 0, 0]) + rng.normal(0, 3e4, (n, 3)); E = np.array([18000.0, 0, 0]) + rng.normal(0, 3e4, (n, 3))
+    env.set_state(P, rng.normal(0, 3.0, (n, 3)), E, rng.normal(0, 3.0, (n, 3)))
+    pursuer = eng.GaussianActorKernel(device=dev).load_state_dict(orthogonal_actor_state(torch, 0))
+    evader = eng.GaussianActorKernel(device=dev).load_state_dict(orthogonal_actor_state(torch, 1))
+    obs_stats, ret_stats = eng.RunningStats(18, dev), eng.RunningStats(1, dev)
+    x0 = env.observe()
+    obs_stats.update_normalize(x0)                                  # statistics of the initial observations
+
+    RING = 8                                                        # rollout ring: obs/act/logp/reward/done per step
+    buf_obs = torch.empty((RING, n, 18), dtype=torch.float32, device=dev)
+    buf_act = torch.empty((RING, n, 3), dtype=torch.float32, device=dev)
+    buf_logp = torch.empty((RING, n, 3), dtype=torch.float32, device=dev)
+    buf_eact = torch.empty((RING, n, 3), dtype=torch.float32, device=dev)
+    buf_elogp = torch.empty((RING, n, 3), dtype=torch.float32, device=dev)
+    buf_rew = torch.empty((RING, n), dtype=torch.float64, device=dev)
+    buf_done = torch.empty((RING, n), dtype=torch.uint8, device=dev)
+    buf_rstd = torch.zeros(RING, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    row_offset = rank * n
+
+    def step(t):
+        k = t % RING
+        pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=t, row_offset=row_offset,
+                       act=buf_act[k], logp=buf_logp[k], obs_out=buf_obs[k])
+        evader.sample(env=env, obs_stats=obs_stats, seed=12, step=t, row_offset=row_offset,
+                      act=buf_eact[k], logp=buf_elogp[k])
+        env.step(buf_act[k], buf_eact[k], reward=buf_rew[k], done=buf_done[k], obs_stats=obs_stats,
+                 ret_stats=ret_stats, ret_std_out=buf_rstd[k:k + 1])
+    LAUNCHES_PER_STEP = 4   # actor x2, env step, statistics merge
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for t in range(args.warmup):
+        step(t)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                               # evict L2 between timed steps
+        ev[i][0].record()
+        step(args.warmup + i)
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t_all = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    total_ms = float(t_all.item())
+    ms_per_step = total_ms / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # ---------------- per-kernel timings (each kernel alone, CUDA events on the launch stream)
+    def time_kernel(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts)), float(np.min(ts))
+
+    k = 0
+    t_env, t_env_min = time_kernel(lambda: env.step(buf_act[k], buf_eact[k], reward=buf_rew[k], done=buf_done[k]))
+    t_act, t_act_min = time_kernel(lambda: pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=0, act=buf_act[k], logp=buf_logp[k]))
+    nk1 = 1 << 20
+    xk1, _ = eng.alloc_soa(6, nk1, torch.float64, dev)
+    ang = torch.rand(nk1, device=dev, dtype=torch.float64) * 6.283185307179586
+    xk1[0], xk1[1], xk1[2] = 7000 * torch.cos(ang), 7000 * torch.sin(ang), 100 * torch.randn(nk1, device=dev, dtype=torch.float64)
+    xk1[3], xk1[4], xk1[5] = -7.5 * torch.sin(ang), 7.5 * torch.cos(ang), 0.1 * torch.randn(nk1, device=dev, dtype=torch.float64)
+    t_k1, t_k1_min = time_kernel(lambda: eng.rk4_propagate(xk1, 1.0, 100))
+    peak64 = eng.measure_vector_peak("fp64")
+    peak32 = eng.measure_vector_peak("fp32")
+    ach_env = FLOP_ENV_STEP * (S / 100.0) * n / (t_env * 1e-3) / 1e12
+    ach_k1 = FLOP_RK4_J2 * 100 * nk1 / (t_k1 * 1e-3) / 1e12
+    ach_act = FLOP_ACTOR * n / (t_act * 1e-3) / 1e12
+
+    # ---------------- e2e through the host-buffer API (pinned host actions in, obs/reward/done out)
+    e2e = None
+    if rank == 0 or world > 1:
+        pa_h = rng.uniform(-1.6, 1.6, (n, 3)).astype(np.float32)
+        ea_h = rng.uniform(-1.6, 1.6, (n, 3)).astype(np.float32)
+        for _ in range(2):
+            env.step_host(pa_h, ea_h)
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(3, min(args.steps, 10))
+        for _ in range(ke):
+            env.step_host(pa_h, ea_h)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world * ke / float(dt.item()), "unit": "env-steps/s",
+               "h2d_bytes_per_step": env.h2d_bytes_per_step, "d2h_bytes_per_step": env.d2h_bytes_per_step,
+               "api": "EnvBatch.step_host(pa, ea) -> (obs, reward, done): numpy in/out via pinned staging -> sat_env_step_host"}
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        return
+    # ---------------- CPU baseline on a bounded sample of the same workload (env step only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        probe, _ = cpu_env_steps_per_s(8 * cores, 1, S, cores)
+        n_cpu = int(max(cores, min(65536, probe * 5.0)))
+        rate, dt = cpu_env_steps_per_s(n_cpu, 3, S, cores)
+        cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} envs x 3 steps of the same env step (S={S} RK4+J2 substeps both craft + danger zone + reward), "
+                         f"CPU oracle port in C with OpenMP on all {cores} host threads, {dt:.1f} s"}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+    line = {
+        "metric": "rk4_env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "envs_per_gpu": n, "substeps": S, "h": 1.0, "j2": True,
+                   "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
+                   "timing": "CUDA events per step on the launch stream, sum over steps, max over ranks",
+                   "rk4_steps_per_sec": value * 2 * S},
+        "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+        "wall_s_timed_region": wall,
+        "e2e": e2e,
+        "roofline": {"kernel": "env_step_kernel<rk4> (fused impulse + 2x100 RK4+J2 substeps + terminal + danger zone + reward + stats)",
+                     "bound": "fp64", "achieved": ach_env, "peak": peak64, "unit": "TFLOP/s", "frac": ach_env / peak64,
+                     "traffic": None, "peak_source": "DFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                     "algorithmic_flops_per_env_step": FLOP_ENV_STEP * (S / 100.0), "launch_ms": t_env, "launch_ms_min": t_env_min,
+                     "hbm_achieved_gbs": BYTES_ENV_STEP * n / (t_env * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak},
+        "kernels": {
+            "rk4_kernel (K1, 2^20 states x 100 substeps, J2)": {"ms": t_k1, "bound": "fp64", "achieved_tflops": ach_k1,
+                                                              "frac_of_measured_fp64_peak": ach_k1 / peak64,
+                                                              "rk4_steps_per_sec": 100 * nk1 / (t_k1 * 1e-3)},
+            "actor_kernel (K3, one actor)": {"ms": t_act, "bound": "fp32", "achieved_tflops": ach_act,
+                                             "frac_of_measured_fp32_peak": ach_act / peak32},
+            "env_step_kernel<rk4> (K2)": {"ms": t_env, "env_steps_per_sec": n / (t_env * 1e-3)},
+            "measured_fp64_peak_tflops": peak64, "measured_fp32_peak_tflops": peak32},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,14 @@ int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const in
                  double* obs_stats, double* ret_stats, double* ret_std_out, void* workspace,
                  const SatEnvParams* p, void* stream);
 
+/* batched danger-zone count on explicit inertial states. Replaces
+ * Time_window_of_danger_zone(R0_c, V0_c, R0_t, V0_t, Delta_V_c).calculate_number_of_hanger_area()
+ * (satellite_function.py:18-99, 341-373). rv [n][12] = R0_c, V0_c, R0_t, V0_t; dv [n] = Delta_V_c.
+ * count_out [n]: 0/1/2, or -1 where the reference would raise (circular / parabolic element set).
+ * debug_out (nullable) [n][2][8]: per node rf_max, rf_min, r_ft, alpha(+pi/2), alpha(-pi/2), theta, dVm, f_c. */
+int sat_danger_zone_count(const double* rv, const double* dv, int64_t n, double u_grav, int32_t* count_out,
+                          double* debug_out, void* stream);
+
 /* host-buffer form of step(): actions from host memory, obs_f32/reward/done to host memory.
  * d_io is a caller-provided device staging buffer of sat_env_step_host_bytes(n) bytes. */
 int64_t sat_env_step_host_bytes(int64_t n);

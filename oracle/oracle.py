@@ -61,6 +61,8 @@ def lib():
         L.orc_numerical_iteration.restype = C.c_double
         L.orc_danger_zone.argtypes = [dp, dp, dp, dp, C.c_double, C.c_double]
         L.orc_danger_zone.restype = i32
+        L.orc_danger_zone_debug.argtypes = [dp, dp, dp, dp, C.c_double, C.c_double, dp]
+        L.orc_danger_zone_debug.restype = i32
         L.orc_env_init.argtypes = [C.POINTER(OrcEnv), C.c_double, C.c_double, C.c_double, C.c_double, i32]
         L.orc_env_reset.argtypes = [C.POINTER(OrcEnv), i32, dp]
         L.orc_env_step.argtypes = [C.POINTER(OrcEnv), dp, dp, dp, i32, dp, dp]
@@ -151,6 +153,13 @@ def numerical_iteration(u, dvm, theta, v1x, v1y, h, guess):
 def danger_zone(Rc, Vc, Rt, Vt, dv, u=MU_M):
     Rc, Vc, Rt, Vt = map(_f64, (Rc, Vc, Rt, Vt))
     return lib().orc_danger_zone(_dp(Rc), _dp(Vc), _dp(Rt), _dp(Vt), float(dv), float(u))
+
+
+def danger_zone_debug(Rc, Vc, Rt, Vt, dv, u=MU_M):
+    Rc, Vc, Rt, Vt = map(_f64, (Rc, Vc, Rt, Vt))
+    dbg = np.zeros(16)
+    c = lib().orc_danger_zone_debug(_dp(Rc), _dp(Vc), _dp(Rt), _dp(Vt), float(dv), float(u), _dp(dbg))
+    return c, dbg.reshape(2, 8)
 
 
 # ------------------------------------------------------------------ env

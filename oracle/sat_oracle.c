@@ -299,7 +299,7 @@ typedef struct {
     double a_t, e_t, i_t, omega_t, Omega_t, f0_t;
 } tw_ctx;
 
-static void rf_extreme_point(const tw_ctx* s, double f_cx, double* rf_max_out, double* rf_min_out) {
+static void rf_extreme_point(const tw_ctx* s, double f_cx, double* rf_max_out, double* rf_min_out, double* dbg) {
     const double fai = 0.0;                                 /* :33 */
     double Delta_Vm = 0, beta = 0, theta = 0;               /* :464 */
     double df = f_cx - s->f0_c;
@@ -315,7 +315,7 @@ static void rf_extreme_point(const tw_ctx* s, double f_cx, double* rf_max_out, d
             theta = acos(cos(df) * cos(fai));
         else if ((-ORC_PI <= df && df < 0) || (ORC_PI <= df && df < 2 * ORC_PI))            /* :475 */
             theta = 2 * ORC_PI - acos(cos(df) * cos(fai));
-    } else { *rf_max_out = 0; *rf_min_out = 0; return; }    /* :478 */
+    } else { *rf_max_out = 0; *rf_min_out = 0; if (dbg) { dbg[3] = dbg[4] = dbg[5] = dbg[6] = 0; } return; }    /* :478 */
 
     sq = sqrt(s->u / s->p_c);
     /* first extreme, alpha_guess = +pi/2  :516-531 */
@@ -329,6 +329,7 @@ static void rf_extreme_point(const tw_ctx* s, double f_cx, double* rf_max_out, d
         v_1y_m = sq * (1 + s->e_c * cos(s->f0_c)) * cos(beta) + Delta_Vm * sin(alpha);
         h_m = s->r_c * v_1y_m;
         rf_max = SQ(h_m) / (s->u * (1 - cos(theta)) + h_m * v_1y_m * cos(theta) - h_m * v_1x_m * sin(theta));
+        if (dbg) dbg[3] = alpha;
     }
     /* second extreme, alpha_guess = -pi/2  :534-547 */
     {
@@ -341,6 +342,7 @@ static void rf_extreme_point(const tw_ctx* s, double f_cx, double* rf_max_out, d
         v_1y_m = sq * (1 + s->e_c * cos(s->f0_c)) * cos(beta) + Delta_Vm * sin(alpha);
         h_m = s->r_c * v_1y_m;
         rf_min = SQ(h_m) / (s->u * (1 - cos(theta)) + h_m * v_1y_m * cos(theta) - h_m * v_1x_m * sin(theta));
+        if (dbg) { dbg[4] = alpha; dbg[5] = theta; dbg[6] = Delta_Vm; }
     }
     rf_max = fabs(rf_max); rf_min = fabs(rf_min);           /* :549-554 */
     if (rf_max < rf_min) { double t = rf_min; rf_min = rf_max; rf_max = t; }
@@ -349,6 +351,12 @@ static void rf_extreme_point(const tw_ctx* s, double f_cx, double* rf_max_out, d
 
 int orc_danger_zone(const double R0_c[3], const double V0_c[3], const double R0_t[3], const double V0_t[3],
                     double Delta_V_c, double u) {
+    return orc_danger_zone_debug(R0_c, V0_c, R0_t, V0_t, Delta_V_c, u, 0);
+}
+
+/* dbg (nullable) [2][8]: per node rf_max, rf_min, r_ft, alpha(+pi/2), alpha(-pi/2), theta, dVm, f_c */
+int orc_danger_zone_debug(const double R0_c[3], const double V0_c[3], const double R0_t[3], const double V0_t[3],
+                          double Delta_V_c, double u, double* dbg) {
     tw_ctx s;
     double el[6];
     double temp1, temp2, u_c1, u_c2, u_t1, u_t2, f_c1, f_c2, f_t1, f_t2;
@@ -373,10 +381,14 @@ int orc_danger_zone(const double R0_c[3], const double V0_c[3], const double R0_
     /* calculate_number_of_hanger_area :341-373 */
     f_c1 = u_c1 - s.omega_c; f_c2 = u_c2 - s.omega_c;
     f_t1 = u_t1 - s.omega_t; f_t2 = u_t2 - s.omega_t;
-    rf_extreme_point(&s, f_c1, &rf_max_c1, &rf_min_c1);
-    rf_extreme_point(&s, f_c2, &rf_max_c2, &rf_min_c2);
+    rf_extreme_point(&s, f_c1, &rf_max_c1, &rf_min_c1, dbg);
+    rf_extreme_point(&s, f_c2, &rf_max_c2, &rf_min_c2, dbg ? dbg + 8 : 0);
     r_ft1 = (s.a_t * (1 - SQ(s.e_t))) / (1 + s.e_t * cos(f_t2));            /* :363 (swapped, Q5) */
     r_ft2 = (s.a_t * (1 - SQ(s.e_t))) / (1 + s.e_t * cos(f_t1));            /* :365 */
+    if (dbg) {
+        dbg[0] = rf_max_c1; dbg[1] = rf_min_c1; dbg[2] = r_ft1; dbg[7] = f_c1;
+        dbg[8] = rf_max_c2; dbg[9] = rf_min_c2; dbg[10] = r_ft2; dbg[15] = f_c2;
+    }
     in1 = (rf_min_c1 <= r_ft1 && r_ft1 <= rf_max_c1);
     in2 = (rf_min_c2 <= r_ft2 && r_ft2 <= rf_max_c2);
     if (in1 && in2) return 2;

@@ -56,6 +56,8 @@ double orc_numerical_iteration(double u, double Delta_Vm, double theta, double v
 /* returns 0/1/2, or -1 when the reference would raise (circular / parabolic element sets) */
 int orc_danger_zone(const double R0_c[3], const double V0_c[3], const double R0_t[3], const double V0_t[3],
                     double Delta_V_c, double u);
+int orc_danger_zone_debug(const double R0_c[3], const double V0_c[3], const double R0_t[3], const double V0_t[3],
+                          double Delta_V_c, double u, double* dbg /* nullable [2][8] */);
 
 /* ---- environment (environment.py:26-179 Flag 0, :181-255 Flag 1, :317-396) ---- */
 typedef struct {

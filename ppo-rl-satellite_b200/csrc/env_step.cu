@@ -138,49 +138,13 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
 
     // ---------------- danger-zone count (:150 -> :317-332); each lane: own craft's elements
     const bool need_dz = !done && !p.skip_danger_zone;
-    Elements el_own = {0, 0, 0, 0, 0, 0};
-    int ok = 0;
-    if (need_dz) {
-        double Ri[3], Vi[3];
+    double Ri[3], Vi[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { Ri[k] = __dadd_rn(p.r_cw[k], r[k]); Vi[k] = __dadd_rn(p.v_cw[k], v[k]); }   // :338-341
-        ok = orbital_elements(p.u_grav, Ri, Vi, el_own) ? 1 : 0;
-    }
-    Elements el_oth;
-    el_oth.a = shfl1(el_own.a); el_oth.e = shfl1(el_own.e); el_oth.i = shfl1(el_own.i);
-    el_oth.omega = shfl1(el_own.omega); el_oth.Omega = shfl1(el_own.Omega); el_oth.f = shfl1(el_own.f);
-    const int ok_both = ok & shfl1(ok);
-    int inside = 0;
-    if (need_dz && ok_both) {
-        const Elements& c = craft == 0 ? el_own : el_oth;     // pursuer ("c")
-        const Elements& t = craft == 0 ? el_oth : el_own;     // target  ("t")
-        // calculate_latitudinal_angle, satellite_function.py:326-337
-        double si_t, ci_t, si_c, ci_c, sdo, cdo;
-        sincos(t.i, &si_t, &ci_t); sincos(c.i, &si_c, &ci_c);
-        sincos(c.Omega - t.Omega, &sdo, &cdo);
-        double sdo2, cdo2;
-        sincos(t.Omega - c.Omega, &sdo2, &cdo2);
-        double temp1 = (si_t * sdo) / (ci_t * si_c - si_t * ci_c * cdo);
-        double temp2 = (si_c * sdo2) / (ci_c * si_t - si_c * ci_t * cdo2);
-        if (isnan(temp1) || isnan(temp2)) { temp1 = 1.0; temp2 = 1.0; }      // :331-332
-        const double u_c1 = atan(temp1), u_t1 = atan(temp2);
-        // :352-355; lane 0 -> node 1 (f_c1, r_ft1 uses f_t2), lane 1 -> node 2 (f_c2, r_ft2 uses f_t1) (Q5)
-        const double f_cx = (craft == 0 ? u_c1 : kPi + u_c1) - c.omega;
-        const double f_tx = (craft == 0 ? u_t1 + kPi : u_t1) - t.omega;
-        PursuerOrbit o;
-        o.u = p.u_grav; o.dv = fuel_c; o.e_c = c.e; o.f0_c = c.f;
-        const double one_m_e2 = 1.0 - c.e * c.e;
-        o.r_c = c.a * one_m_e2 / (1.0 + c.e * cos(c.f));                      // :57
-        o.p_c = c.a * one_m_e2;                                               // :58
-        double rf_max, rf_min;
-        rf_extreme_point(o, f_cx, rf_max, rf_min);                            // :359 / :361
-        const double r_ft = (t.a * (1.0 - t.e * t.e)) / (1.0 + t.e * cos(f_tx));   // :363 / :365
-        inside = (rf_min <= r_ft && r_ft <= rf_max) ? 1 : 0;                  // :367-372
-    }
-    const int inside_sum = inside + shfl1(inside);
+    for (int k = 0; k < 3; ++k) { Ri[k] = __dadd_rn(p.r_cw[k], r[k]); Vi[k] = __dadd_rn(p.v_cw[k], v[k]); }   // :338-341
+    const int dz_eval = danger_zone_pair(craft, need_dz, Ri, Vi, fuel_c, p.u_grav, nullptr);
     int dz_new = dz_stale;
     if (need_dz) {
-        if (ok_both) dz_new = inside_sum;
+        if (dz_eval >= 0) dz_new = dz_eval;
         else { dz_new = 0; err = 1; }        // the reference raises here (circular / parabolic element set)
     }
 
@@ -279,6 +243,34 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
         for (int row = 0; row < rows; ++row) { double t = tile[row][dim] - mean; m2 += t * t; }
         partials[((int64_t)blockIdx.x * kStatDims + dim) * 2 + 0] = mean;
         partials[((int64_t)blockIdx.x * kStatDims + dim) * 2 + 1] = m2;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// batched danger-zone count on explicit inertial states (Time_window_of_danger_zone(...)
+// .calculate_number_of_hanger_area(), satellite_function.py:18-99, 341-373)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+danger_zone_kernel(const double* __restrict__ rv, const double* __restrict__ dv, int64_t n, double u_grav,
+                   int32_t* __restrict__ count_out, double* __restrict__ debug_out) {
+    const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t env_raw = tid >> 1;
+    const int craft = (int)(tid & 1);
+    const bool valid = env_raw < n;
+    const int64_t e = valid ? env_raw : n - 1;
+    double Ri[3], Vi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { Ri[k] = rv[e * 12 + craft * 6 + k]; Vi[k] = rv[e * 12 + craft * 6 + 3 + k]; }
+    DzDebug dbg = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int dz = danger_zone_pair(craft, true, Ri, Vi, dv[e], u_grav, debug_out ? &dbg : nullptr);
+    if (valid) {
+        if (craft == 0) count_out[e] = dz;
+        if (debug_out) {
+            double* o = debug_out + (e * 2 + craft) * 8;
+            o[0] = dbg.rf_max; o[1] = dbg.rf_min; o[2] = dbg.r_ft; o[3] = dbg.alpha0; o[4] = dbg.alpha1;
+            o[5] = dbg.theta; o[6] = dbg.dvm; o[7] = dbg.f_cx;
+        }
     }
 }
 
@@ -543,6 +535,15 @@ int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const in
         rc = launch_status();
     }
     return rc;
+}
+
+int sat_danger_zone_count(const double* rv, const double* dv, int64_t n, double u_grav, int32_t* count_out,
+                          double* debug_out, void* stream) {
+    if (!rv || !dv || !count_out) return SAT_ERR_NULL;
+    if (n <= 0) return SAT_ERR_SIZE;
+    const int64_t nblocks = (n + kEnvsPerBlock - 1) / kEnvsPerBlock;
+    danger_zone_kernel<<<(unsigned)nblocks, kBlock, 0, (cudaStream_t)stream>>>(rv, dv, n, u_grav, count_out, debug_out);
+    return launch_status();
 }
 
 int64_t sat_env_step_host_bytes(int64_t n) {

@@ -273,12 +273,16 @@ SAT_DEV double rf_from_alpha(const PursuerOrbit& o, double sq_e_sin, double sq_k
     return (hm * hm) / (o.u * (1.0 - cth) + hm * v1y * cth - hm * v1x * sth);   // :530 / :545
 }
 
-static __device__ __noinline__ void rf_extreme_point(const PursuerOrbit& o, double f_cx, double& rf_max, double& rf_min) {
+struct DzDebug { double rf_max, rf_min, r_ft, alpha0, alpha1, theta, dvm, f_cx; };
+
+static __device__ __noinline__ void rf_extreme_point(const PursuerOrbit& o, double f_cx, double& rf_max, double& rf_min,
+                                                     DzDebug* dbg) {
     double df = f_cx - o.f0_c;
     double sdf, cdf;
     sincos(df, &sdf, &cdf);
     double k = 1.0 + o.e_c * cos(o.f0_c);
     double temp1 = (sdf * sdf) / (o.u * (k * k) / (o.p_c * (o.dv * o.dv)) - 1.0);     // :466 / :481
+    if (dbg) { dbg->alpha0 = 0.0; dbg->alpha1 = 0.0; dbg->theta = 0.0; dbg->dvm = 0.0; }
     if (!(0.0 <= temp1)) { rf_max = 0.0; rf_min = 0.0; return; }                      // :478
     double beta = atan(0.0 / sdf);                                                    // :469, tan(fai) = 0
     double sb = sin(beta), cb = cos(beta);
@@ -305,8 +309,61 @@ static __device__ __noinline__ void rf_extreme_point(const PursuerOrbit& o, doub
         f.sth = sth; f.dvm = dvm;
         double alpha = hybrd1(f, ag);                                                 // :523 / :540
         r[j] = fabs(rf_from_alpha(o, sq_e_sin, sq_k, dvm, alpha, cth, sth));          // :549-550
+        if (dbg) { if (j == 0) dbg->alpha0 = alpha; else dbg->alpha1 = alpha; }
     }
+    if (dbg) { dbg->theta = theta; dbg->dvm = dvm; }
     if (r[0] < r[1]) { rf_max = r[1]; rf_min = r[0]; } else { rf_max = r[0]; rf_min = r[1]; }   // :551-554
+}
+
+
+// ------------------------------------------------------------------------------------------
+// danger-zone count for one environment evaluated by a LANE PAIR (even lane = pursuer "c", odd lane =
+// target "t"): environment.py:317-332 -> satellite_function.py:18-99, 317-373. Each lane converts its own
+// craft to orbital elements, the pair swaps them with shfl.xor 1, and each lane then solves one of the two
+// relative-node reachability problems (lane 0: node 1, lane 1: node 2). MUST be called by all 32 lanes of
+// the warp (the shuffles are warp-wide); `active` predicates the work.
+// Returns 0/1/2, or -1 when the reference would raise (circular / parabolic element set).
+// ------------------------------------------------------------------------------------------
+SAT_DEV int danger_zone_pair(int craft, bool active, const double Ri[3], const double Vi[3], double fuel_c,
+                             double u_grav, DzDebug* dbg) {
+    Elements el_own = {0, 0, 0, 0, 0, 0};
+    int ok = 0;
+    if (active) ok = orbital_elements(u_grav, Ri, Vi, el_own) ? 1 : 0;
+    Elements el_oth;
+    el_oth.a = __shfl_xor_sync(0xffffffffu, el_own.a, 1); el_oth.e = __shfl_xor_sync(0xffffffffu, el_own.e, 1);
+    el_oth.i = __shfl_xor_sync(0xffffffffu, el_own.i, 1); el_oth.omega = __shfl_xor_sync(0xffffffffu, el_own.omega, 1);
+    el_oth.Omega = __shfl_xor_sync(0xffffffffu, el_own.Omega, 1); el_oth.f = __shfl_xor_sync(0xffffffffu, el_own.f, 1);
+    const int ok_both = ok & __shfl_xor_sync(0xffffffffu, ok, 1);
+    int inside = 0;
+    if (active && ok_both) {
+        const Elements& c = craft == 0 ? el_own : el_oth;     // pursuer
+        const Elements& t = craft == 0 ? el_oth : el_own;     // target
+        // calculate_latitudinal_angle, satellite_function.py:326-337
+        double si_t, ci_t, si_c, ci_c, sdo, cdo, sdo2, cdo2;
+        sincos(t.i, &si_t, &ci_t); sincos(c.i, &si_c, &ci_c);
+        sincos(c.Omega - t.Omega, &sdo, &cdo);
+        sincos(t.Omega - c.Omega, &sdo2, &cdo2);
+        double temp1 = (si_t * sdo) / (ci_t * si_c - si_t * ci_c * cdo);
+        double temp2 = (si_c * sdo2) / (ci_c * si_t - si_c * ci_t * cdo2);
+        if (isnan(temp1) || isnan(temp2)) { temp1 = 1.0; temp2 = 1.0; }      // :331-332
+        const double u_c1 = atan(temp1), u_t1 = atan(temp2);
+        // :352-355; lane 0 -> node 1 (f_c1, r_ft1 uses f_t2), lane 1 -> node 2 (f_c2, r_ft2 uses f_t1) (Q5)
+        const double f_cx = (craft == 0 ? u_c1 : kPi + u_c1) - c.omega;
+        const double f_tx = (craft == 0 ? u_t1 + kPi : u_t1) - t.omega;
+        PursuerOrbit o;
+        o.u = u_grav; o.dv = fuel_c; o.e_c = c.e; o.f0_c = c.f;
+        const double one_m_e2 = 1.0 - c.e * c.e;
+        o.r_c = c.a * one_m_e2 / (1.0 + c.e * cos(c.f));                      // :57
+        o.p_c = c.a * one_m_e2;                                               // :58
+        double rf_max, rf_min;
+        rf_extreme_point(o, f_cx, rf_max, rf_min, dbg);                       // :359 / :361
+        const double r_ft = (t.a * (1.0 - t.e * t.e)) / (1.0 + t.e * cos(f_tx));   // :363 / :365
+        inside = (rf_min <= r_ft && r_ft <= rf_max) ? 1 : 0;                  // :367-372
+        if (dbg) { dbg->rf_max = rf_max; dbg->rf_min = rf_min; dbg->r_ft = r_ft; dbg->f_cx = f_cx; }
+    }
+    const int inside_sum = inside + __shfl_xor_sync(0xffffffffu, inside, 1);
+    if (!active) return 0;
+    return ok_both ? inside_sum : -1;
 }
 
 // ------------------------------------------------------------------------------------------

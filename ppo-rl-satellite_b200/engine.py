@@ -279,6 +279,19 @@ class EnvBatch:
         return self.istate[L.ICOL_ERR]
 
 
+def danger_zone_count(rv, dv, u=MU_M, debug=False):
+    """Batched Time_window_of_danger_zone(...).calculate_number_of_hanger_area() (satellite_function.py:341-373).
+    rv: CUDA fp64 [n,12] = (R0_c, V0_c, R0_t, V0_t) inertial, metres; dv: [n] Delta_V_c. -> int32 [n]."""
+    torch = L.require_cuda()
+    rv, dv = rv.contiguous(), dv.contiguous()
+    n = rv.shape[0]
+    out = torch.empty(n, dtype=torch.int32, device=rv.device)
+    dbg = torch.zeros((n, 2, 8), dtype=torch.float64, device=rv.device) if debug else None
+    L.check(L.load().sat_danger_zone_count(L.ptr(rv), L.ptr(dv), n, float(u), L.ptr(out), L.ptr(dbg), L.stream_ptr()),
+            "sat_danger_zone_count")
+    return (out, dbg) if debug else out
+
+
 # --------------------------------------------------------------------------------------------- K3
 class GaussianActorKernel:
     """Fused Actor_Gaussian forward + sampling (ppo_continuous.py:83-95, 176-189) for batches."""
