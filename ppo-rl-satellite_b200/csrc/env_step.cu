@@ -8,9 +8,14 @@
 //
 // Mapping: TWO lanes per environment (even lane = pursuer, odd lane = escaper). Each lane owns one
 // craft through impulse + propagation + orbital elements, the pair exchanges results with
-// __shfl_xor(…, 1), and each lane then evaluates one of the two relative-node reachability
-// solves. 64-thread CTAs (32 envs) keep the CTA count a near-multiple of 148 SMs x resident CTAs
-// at the headline batch (65 536 envs -> 2048 CTAs = 13.8 per SM).
+// __shfl_xor(…, 1), and each lane then sets up one of the two relative-node reachability problems;
+// the fsolve work items are compacted across the CTA through a shared-memory queue.
+//   cw  mode: ONE kernel (propagation is a 6x6 product).
+//   rk4 mode: kernel A = clip/gate/impulse + S RK4 substeps in registers (FP64-pipe bound, 72 registers,
+//             64-thread CTAs so the whole 65 536-env batch (2048 CTAs) is resident at 14 CTAs/SM);
+//             kernel B = everything after the propagation (register-heavy, divergent). The split costs one
+//             extra read of the state (~130 B/env, ~1 us at 65 536 envs) and lets each half run at its own
+//             occupancy.
 //
 // Data layout in HBM: SoA fp64 columns [16][ld] + int32 columns [4][ld] (include/satb200.h).
 // Compiled with -fmad=false: the env arithmetic must round exactly like numpy's.
@@ -22,25 +27,176 @@ namespace {
 
 using namespace sat;
 
-constexpr int kBlock = 64;              // threads per CTA
+constexpr int kBlock = 128;             // finish / fused kernels: threads per CTA (2 lanes per env)
 constexpr int kEnvsPerBlock = kBlock / 2;
+constexpr int kFrontBlock = 64;         // rk4 front (impulse + propagation) kernel
 constexpr int kObs = 18;
 constexpr int kStatDims = 19;           // 18 observation dims + discounted return
+constexpr int kWsHeader = 256;          // workspace: [ticket counter | pad] [dis_prev: n doubles] [partials]
 
 SAT_DEV double shfl1(double v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
 SAT_DEV int shfl1(int v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
 
 SAT_DEV double clip16(double a) { return a < -1.6 ? -1.6 : (a > 1.6 ? 1.6 : a); }   // np.clip, environment.py:86-87
 
-template <int MODE, typename ActT>
+__host__ __device__ inline int64_t ws_disprev_offset() { return kWsHeader; }
+__host__ __device__ inline int64_t ws_partials_offset(int64_t n) { return kWsHeader + ((n * 8 + 255) / 256) * 256; }
+
+// ---------------------------------------------------------------------------------------------
+// front half of step(): clip, gate, impulse (with the int64 truncation quirk), fuel, propagation of the
+// lane's own craft. environment.py:86-121 (Flag 0) / :185-210 (Flag 1).
+// ---------------------------------------------------------------------------------------------
+struct Lane {
+    double r[3], v[3];      // own craft, relative frame
+    double a[3];            // own clipped + gated action
+    double fuel_own;
+    double dis_prev;        // |P - E| before the step (:89)
+};
+
+template <typename ActT>
+SAT_DEV void load_and_gate(const SatEnvState& st, const SatEnvParams& p, const ActT* __restrict__ pa,
+                           const ActT* __restrict__ ea, int64_t e, int craft, Lane& L, bool do_impulse) {
+    const int64_t ld = st.ld;
+    const double* __restrict__ S = st.state;
+    const int32_t* __restrict__ I = st.istate;
+    const int base = craft * 6;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { L.r[k] = S[(base + k) * ld + e]; L.v[k] = S[(base + 3 + k) * ld + e]; }
+    L.fuel_own = S[(SAT_COL_FUEL_C + craft) * ld + e];
+    const double dis_stale = S[SAT_COL_DIS * ld + e];
+    const int dz_stale = I[SAT_ICOL_DZ * ld + e];
+    const int int_state = I[SAT_ICOL_INTSTATE * ld + e];
+    {
+        const ActT* act = craft ? ea : pa;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) L.a[k] = clip16((double)act[e * 3 + k]);
+    }
+    bool frozen;                                            // gating uses LAST step's dis / dangerous_zone (Q3)
+    if (p.flag == 0) frozen = (craft == 0) && (dis_stale < p.d_range) && (dz_stale != 0);   // :91-96
+    else frozen = (craft == 1) && (dz_stale == 0);                                          // :190-198
+    if (frozen) { L.a[0] = 0.0; L.a[1] = 0.0; L.a[2] = 0.0; }
+    if (!do_impulse) return;
+    double d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double o = shfl1(L.r[k]);
+        d[k] = craft == 0 ? __dsub_rn(L.r[k], o) : __dsub_rn(o, L.r[k]);
+    }
+    L.dis_prev = norm3(d);                                  // :89
+    // right after reset() the arrays are int64 and `+=` truncates toward zero (Q1)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double s = __dadd_rn(L.v[k], L.a[k]);
+        L.v[k] = int_state ? trunc(s) : s;
+    }
+    L.fuel_own = __dsub_rn(L.fuel_own, __dadd_rn(__dadd_rn(fabs(L.a[0]), fabs(L.a[1])), fabs(L.a[2])));   // :106-107
+}
+
+SAT_DEV void propagate_cw(const SatEnvParams& p, Lane& L) {
+    const double x6[6] = {L.r[0], L.r[1], L.r[2], L.v[0], L.v[1], L.v[2]};
+    double y6[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y6[i] = gemv6_row(p.stm + 6 * i, x6);      // satellite_function.py:778-779
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { L.r[k] = y6[k]; L.v[k] = y6[3 + k]; }
+}
+
+SAT_DEV void propagate_rk4(const SatEnvParams& p, Lane& L) {
+    double X[3], V[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { X[k] = p.r_cw[k] + L.r[k]; V[k] = p.v_cw[k] + L.v[k]; }
+    const Rk4Consts c = make_rk4_consts(p.h, p.mu, p.re, p.j2);
+    if (p.j2 != 0.0) {
+#pragma unroll 1
+        for (int s = 0; s < p.substeps; ++s) rk4_step<true>(X, V, c);
+    } else {
+#pragma unroll 1
+        for (int s = 0; s < p.substeps; ++s) rk4_step<false>(X, V, c);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { L.r[k] = X[k] - p.r_cw[k]; L.v[k] = V[k] - p.v_cw[k]; }
+}
+
+// rk4 mode, kernel A: impulse + S RK4 substeps, state written back; |P-E| before the step goes to the workspace.
+// 64-thread CTAs at <= 72 registers: all 2048 CTAs of the 65 536-env batch are resident at once (14 per SM).
+template <typename ActT>
+__global__ void __launch_bounds__(kFrontBlock, 14)
+env_front_rk4_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* __restrict__ ea,
+                     double* __restrict__ dis_prev_out, const __grid_constant__ SatEnvParams p) {
+    const int64_t tid = (int64_t)blockIdx.x * kFrontBlock + threadIdx.x;
+    const int64_t env_raw = tid >> 1;
+    const int craft = (int)(tid & 1);
+    const bool valid = env_raw < st.n;
+    const int64_t e = valid ? env_raw : st.n - 1;
+    Lane L;
+    load_and_gate(st, p, pa, ea, e, craft, L, true);
+    propagate_rk4(p, L);
+    if (valid) {
+        const int64_t ld = st.ld;
+        const int base = craft * 6;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { st.state[(base + k) * ld + e] = L.r[k]; st.state[(base + 3 + k) * ld + e] = L.v[k]; }
+        st.state[(SAT_COL_FUEL_C + craft) * ld + e] = L.fuel_own;
+        if (craft == 0) dis_prev_out[e] = L.dis_prev;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-wide compaction of the fsolve work items: every lane with a reachable node pushes two root problems
+// into a shared-memory queue; the queue is then processed densely (thread t <- task t), so warps beyond
+// the task count skip the solver entirely instead of running it with ~1/4 of their lanes active.
+// ---------------------------------------------------------------------------------------------
+struct SolveQueue {
+    double A[2 * kBlock], sth[2 * kBlock], dvm[2 * kBlock], alpha[2 * kBlock];
+    int warp_count[kBlock / 32];
+};
+
+SAT_DEV int queue_push(SolveQueue& q, const DzNode& nd) {
+    // returns this lane's first task index (tasks idx, idx+1), or -1; contains __syncthreads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool has = nd.status == 2;
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    if (lane == 0) q.warp_count[warp] = __popc(m);
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) base += (w < warp) ? q.warp_count[w] : 0;
+    int idx = -1;
+    if (has) {
+        idx = 2 * (base + __popc(m & ((1u << lane) - 1u)));
+        q.A[idx] = nd.A0; q.A[idx + 1] = nd.A1;
+        q.sth[idx] = nd.sth; q.sth[idx + 1] = nd.sth;
+        q.dvm[idx] = nd.dvm; q.dvm[idx + 1] = nd.dvm;
+    }
+    __syncthreads();
+    return idx;
+}
+
+SAT_DEV void queue_run(SolveQueue& q) {
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) total += q.warp_count[w];
+    total *= 2;
+    for (int t = threadIdx.x; t < total; t += kBlock) q.alpha[t] = dz_solve(q.A[t], q.sth[t], q.dvm[t], t & 1);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// back half of step(): exchange, distance, terminal checks, danger zone, reward, observation, statistics
+// partials, auto-reset. environment.py:130-179 / :212-255, :317-343, :346-396.
+// FUSED = true: front half in the same kernel (cw mode, where propagation is one 6x6 product).
+// ---------------------------------------------------------------------------------------------
+template <bool FUSED, typename ActT>
 __global__ void __launch_bounds__(kBlock)
 env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* __restrict__ ea,
                 const int32_t* __restrict__ count_override, float* __restrict__ obs_f32,
                 double* __restrict__ obs_f64, double* __restrict__ term_obs_f64,
                 double* __restrict__ reward_out, uint8_t* __restrict__ done_out,
-                double* __restrict__ partials, const __grid_constant__ SatEnvParams p) {
+                const double* __restrict__ dis_prev_in, double* __restrict__ partials,
+                unsigned int* __restrict__ ticket, const __grid_constant__ SatEnvParams p) {
     __shared__ double tile[kEnvsPerBlock][kStatDims];        // next observation (+ return) of the CTA's envs
     __shared__ double tile_term[kEnvsPerBlock][kObs];        // pre-reset observation
+    __shared__ SolveQueue queue;
 
     const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const int64_t env_raw = tid >> 1;
@@ -50,79 +206,25 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     const int64_t ld = st.ld;
     double* __restrict__ S = st.state;
     int32_t* __restrict__ I = st.istate;
+    if (ticket && blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;   // consumed by stats_merge_kernel (next in stream)
 
-    // ---------------- load own craft + env scalars
-    double r[3], v[3];
-    const int base = craft * 6;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { r[k] = S[(base + k) * ld + e]; v[k] = S[(base + 3 + k) * ld + e]; }
-    double fuel_own = S[(SAT_COL_FUEL_C + craft) * ld + e];
-    const double dis_stale = S[SAT_COL_DIS * ld + e];
-    double ret = S[SAT_COL_RET * ld + e];
+    Lane L;
+    load_and_gate(st, p, pa, ea, e, craft, L, FUSED);
+    if (FUSED) propagate_cw(p, L);
+    else L.dis_prev = dis_prev_in[e];
+    const double dz_dummy = 0.0; (void)dz_dummy;
     const int dz_stale = I[SAT_ICOL_DZ * ld + e];
     const int count = I[SAT_ICOL_COUNT * ld + e];
-    const int int_state = I[SAT_ICOL_INTSTATE * ld + e];
     int err = I[SAT_ICOL_ERR * ld + e];
-
-    // ---------------- actions: clip, gate (environment.py:86-104 / :185-198)
-    double a[3];
-    {
-        const ActT* act = craft ? ea : pa;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) a[k] = clip16((double)act[e * 3 + k]);
-    }
-    bool frozen;
-    if (p.flag == 0) frozen = (craft == 0) && (dis_stale < p.d_range) && (dz_stale != 0);
-    else frozen = (craft == 1) && (dz_stale == 0);
-    if (frozen) { a[0] = 0.0; a[1] = 0.0; a[2] = 0.0; }
-
-    // previous distance (:89) needs the other craft's position
-    double o_r[3], o_v[3], d[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) o_r[k] = shfl1(r[k]);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) d[k] = craft == 0 ? __dsub_rn(r[k], o_r[k]) : __dsub_rn(o_r[k], r[k]);
-    const double dis_prev = norm3(d);
-
-    // impulse; right after reset() the arrays are int64 and `+=` truncates toward zero (Q1)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        double s = __dadd_rn(v[k], a[k]);
-        v[k] = int_state ? trunc(s) : s;
-    }
-    fuel_own = __dsub_rn(fuel_own, __dadd_rn(__dadd_rn(fabs(a[0]), fabs(a[1])), fabs(a[2])));   // :106-107
-
-    // ---------------- propagate own craft
-    if (MODE == SAT_MODE_CW) {
-        double x6[6] = {r[0], r[1], r[2], v[0], v[1], v[2]}, y6[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) y6[i] = gemv6_row(p.stm + 6 * i, x6);     // satellite_function.py:778-779
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { r[k] = y6[k]; v[k] = y6[3 + k]; }
-    } else {
-        double X[3], V[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { X[k] = p.r_cw[k] + r[k]; V[k] = p.v_cw[k] + v[k]; }
-        const Rk4Consts c = make_rk4_consts(p.h, p.mu, p.re, p.j2);
-        if (p.j2 != 0.0) {
-#pragma unroll 1
-            for (int s = 0; s < p.substeps; ++s) rk4_step<true>(X, V, c);
-        } else {
-#pragma unroll 1
-            for (int s = 0; s < p.substeps; ++s) rk4_step<false>(X, V, c);
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { r[k] = X[k] - p.r_cw[k]; v[k] = V[k] - p.v_cw[k]; }
-    }
+    const double ret = S[SAT_COL_RET * ld + e];
 
     // ---------------- exchange, distance, terminal checks (:130-147)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { o_r[k] = shfl1(r[k]); o_v[k] = shfl1(v[k]); }
-    double P[3], Pv[3], E[3], Ev[3];
+    double P[3], Pv[3], E[3], Ev[3], d[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        P[k] = craft == 0 ? r[k] : o_r[k];  Pv[k] = craft == 0 ? v[k] : o_v[k];
-        E[k] = craft == 0 ? o_r[k] : r[k];  Ev[k] = craft == 0 ? o_v[k] : v[k];
+        const double o_r = shfl1(L.r[k]), o_v = shfl1(L.v[k]);
+        P[k] = craft == 0 ? L.r[k] : o_r;  Pv[k] = craft == 0 ? L.v[k] : o_v;
+        E[k] = craft == 0 ? o_r : L.r[k];  Ev[k] = craft == 0 ? o_v : L.v[k];
         d[k] = __dsub_rn(P[k], E[k]);
     }
     const double dis = norm3(d);                                              // :132
@@ -130,19 +232,26 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     const bool captured = dis <= p.d_capture;                                 // :139
     const bool timeout = count_new >= p.max_episode_steps;                    // :144
     const bool done = captured || timeout;
-    const double fuel_oth = shfl1(fuel_own);
-    const double fuel_c = craft == 0 ? fuel_own : fuel_oth;                   // Delta_V_c = fuel_c (:328)
+    const double fuel_oth = shfl1(L.fuel_own);
+    const double fuel_c = craft == 0 ? L.fuel_own : fuel_oth;                 // Delta_V_c = fuel_c (:328)
     double pa_gated[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { double o = shfl1(a[k]); pa_gated[k] = craft == 0 ? a[k] : o; }
+    for (int k = 0; k < 3; ++k) { const double o = shfl1(L.a[k]); pa_gated[k] = craft == 0 ? L.a[k] : o; }
 
-    // ---------------- danger-zone count (:150 -> :317-332); each lane: own craft's elements
+    // ---------------- danger-zone count (:150 -> :317-332), three phases with CTA-wide solve compaction
     const bool need_dz = !done && !p.skip_danger_zone;
-    double Ri[3], Vi[3];
+    DzNode nd;
+    {
+        double Ri[3], Vi[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { Ri[k] = __dadd_rn(p.r_cw[k], r[k]); Vi[k] = __dadd_rn(p.v_cw[k], v[k]); }   // :338-341
-    const int dz_eval = danger_zone_pair(craft, need_dz, Ri, Vi, fuel_c, p.u_grav, nullptr);
-    int dz_new = dz_stale;
+        for (int k = 0; k < 3; ++k) { Ri[k] = __dadd_rn(p.r_cw[k], L.r[k]); Vi[k] = __dadd_rn(p.v_cw[k], L.v[k]); }   // :338-341
+        dz_prepare(craft, need_dz, Ri, Vi, fuel_c, p.u_grav, nd);
+    }
+    const int qidx = queue_push(queue, nd);
+    queue_run(queue);
+    const double alpha0 = qidx >= 0 ? queue.alpha[qidx] : 0.0, alpha1 = qidx >= 0 ? queue.alpha[qidx + 1] : 0.0;
+    const int dz_eval = dz_finalize(need_dz, nd, alpha0, alpha1, nullptr);
+    int dz_new = dz_stale;                                   // not refreshed on capture / time-out steps (Q3)
     if (need_dz) {
         if (dz_eval >= 0) dz_new = dz_eval;
         else { dz_new = 0; err = 1; }        // the reference raises here (circular / parabolic element set)
@@ -153,7 +262,7 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     if (captured) reward = (p.flag == 0) ? 100.0 : -150.0;
     else if (timeout) reward = (p.flag == 0) ? 0.0 : 100.0;
     else {
-        const double ra = (dis < dis_prev) ? 1.0 : -1.0;                                      // :161
+        const double ra = (dis < L.dis_prev) ? 1.0 : -1.0;                                    // :161
         const double rb = (p.d_capture <= dis && dis <= 4.0 * p.d_capture) ? -1.0 : -2.0;     // :162
         const double rc = (dz_new == 0) ? -1.0 : dz_new * 0.5;                                // :164
         const double pv1 = cosine3(P, E);                                                     // :166
@@ -185,20 +294,24 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
 
     // ---------------- auto reset (environment.py:66-79; fuel/dis/dangerous_zone persist, Q2)
     int int_state_new = 0, count_store = count_new;
-    if (done && p.auto_reset) {
+    const bool reset_now = done && p.auto_reset;
+    if (reset_now) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             P[k] = p.reset_p[k]; E[k] = p.reset_e[k]; Pv[k] = 0.0; Ev[k] = 0.0;
-            r[k] = craft == 0 ? P[k] : E[k]; v[k] = 0.0;
+            L.r[k] = craft == 0 ? P[k] : E[k]; L.v[k] = 0.0;
         }
         int_state_new = 1; count_store = 0;
     }
 
     // ---------------- store state
     if (valid) {
+        const int base = craft * 6;
+        if (FUSED || reset_now) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { S[(base + k) * ld + e] = r[k]; S[(base + 3 + k) * ld + e] = v[k]; }
-        S[(SAT_COL_FUEL_C + craft) * ld + e] = fuel_own;
+            for (int k = 0; k < 3; ++k) { S[(base + k) * ld + e] = L.r[k]; S[(base + 3 + k) * ld + e] = L.v[k]; }
+        }
+        if (FUSED) S[(SAT_COL_FUEL_C + craft) * ld + e] = L.fuel_own;
         if (craft == 0) {
             S[SAT_COL_DIS * ld + e] = dis;
             S[SAT_COL_RET * ld + e] = done ? 0.0 : ret_new;
@@ -246,7 +359,6 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     }
 }
 
-
 // ---------------------------------------------------------------------------------------------
 // batched danger-zone count on explicit inertial states (Time_window_of_danger_zone(...)
 // .calculate_number_of_hanger_area(), satellite_function.py:18-99, 341-373)
@@ -254,6 +366,7 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
 __global__ void __launch_bounds__(kBlock)
 danger_zone_kernel(const double* __restrict__ rv, const double* __restrict__ dv, int64_t n, double u_grav,
                    int32_t* __restrict__ count_out, double* __restrict__ debug_out) {
+    __shared__ SolveQueue queue;
     const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const int64_t env_raw = tid >> 1;
     const int craft = (int)(tid & 1);
@@ -262,8 +375,13 @@ danger_zone_kernel(const double* __restrict__ rv, const double* __restrict__ dv,
     double Ri[3], Vi[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { Ri[k] = rv[e * 12 + craft * 6 + k]; Vi[k] = rv[e * 12 + craft * 6 + 3 + k]; }
+    DzNode nd;
+    dz_prepare(craft, true, Ri, Vi, dv[e], u_grav, nd);
+    const int qidx = queue_push(queue, nd);
+    queue_run(queue);
+    const double alpha0 = qidx >= 0 ? queue.alpha[qidx] : 0.0, alpha1 = qidx >= 0 ? queue.alpha[qidx + 1] : 0.0;
     DzDebug dbg = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int dz = danger_zone_pair(craft, true, Ri, Vi, dv[e], u_grav, debug_out ? &dbg : nullptr);
+    const int dz = dz_finalize(true, nd, alpha0, alpha1, debug_out ? &dbg : nullptr);
     if (valid) {
         if (craft == 0) count_out[e] = dz;
         if (debug_out) {
@@ -276,7 +394,8 @@ danger_zone_kernel(const double* __restrict__ rv, const double* __restrict__ dv,
 
 // ---------------------------------------------------------------------------------------------
 // merge of per-CTA partials into the running statistics (RunningMeanStd, normalization.py:19-29).
-// One warp per statistic dimension, fixed merge order -> bitwise deterministic.
+// One CTA per statistic dimension; two-pass (grand mean, then M2 about it) with fixed summation order ->
+// bitwise deterministic. The last CTA to finish (ticket) advances the sample counts.
 // ---------------------------------------------------------------------------------------------
 struct Moments { double n, mean, m2; };
 SAT_DEV Moments chan(Moments A, Moments B) {
@@ -292,8 +411,8 @@ SAT_DEV Moments chan(Moments A, Moments B) {
 
 SAT_DEV void fold_into_running(double* stats, int dim, int d, Moments B, double* std_out) {
     // stats: [0]=n, mean[dim], S[dim], std[dim]
-    double n_old = stats[0];
-    double mean_old = stats[1 + d], S_old = stats[1 + dim + d];
+    const double n_old = stats[0];
+    const double mean_old = stats[1 + d], S_old = stats[1 + dim + d];
     double n_new, mean_new, S_new, std_new;
     if (B.n == 1.0) {
         // literal Welford step of the reference incl. its first-sample rule (normalization.py:21-29)
@@ -313,40 +432,56 @@ SAT_DEV void fold_into_running(double* stats, int dim, int d, Moments B, double*
     }
     stats[1 + d] = mean_new; stats[1 + dim + d] = S_new; stats[1 + 2 * dim + d] = std_new;
     if (std_out) *std_out = std_new;
-    (void)n_new;
 }
 
-__global__ void stats_merge_kernel(const double* __restrict__ partials, int64_t nblocks, int64_t n_rows,
-                                   int rows_per_block, int ndims_in_partials,
-                                   double* obs_stats, int obs_dim, double* ret_stats, double* ret_std_out) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool active = warp < ndims_in_partials;
-    Moments acc = {0.0, 0.0, 0.0};
-    for (int64_t b = lane; active && b < nblocks; b += 32) {
-        int64_t rem = n_rows - b * rows_per_block;
-        Moments B;
-        B.n = (double)(rem < rows_per_block ? rem : rows_per_block);
-        B.mean = partials[(b * ndims_in_partials + warp) * 2 + 0];
-        B.m2 = partials[(b * ndims_in_partials + warp) * 2 + 1];
-        acc = chan(acc, B);
-    }
+constexpr int kMergeThreads = 256;
+
+SAT_DEV double block_sum_fixed(double v, double* sm) {
+    // warp tree (xor) then the per-warp sums added in warp order by every thread: fixed order, all threads get the result
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        Moments O;
-        O.n = __shfl_xor_sync(0xffffffffu, acc.n, off);
-        O.mean = __shfl_xor_sync(0xffffffffu, acc.mean, off);
-        O.m2 = __shfl_xor_sync(0xffffffffu, acc.m2, off);
-        // keep a fixed (lower lane first) operand order so both partners compute the same value
-        acc = (lane & off) ? chan(O, acc) : chan(acc, O);
-    }
-    if (active && lane == 0) {
-        if (warp < obs_dim) { if (obs_stats) fold_into_running(obs_stats, obs_dim, warp, acc, nullptr); }
-        else if (ret_stats) fold_into_running(ret_stats, 1, 0, acc, ret_std_out);
-    }
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kMergeThreads / 32; ++w) t += sm[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+stats_merge_kernel(const double* __restrict__ partials, int64_t nblocks, int64_t n_rows, int rows_per_block,
+                   int ndims_in_partials, double* obs_stats, int obs_dim, double* ret_stats, double* ret_std_out,
+                   unsigned int* ticket) {
+    __shared__ double sm[kMergeThreads / 32];
+    const int dim = blockIdx.x;                  // gridDim.x == ndims_in_partials
+    const double N = (double)n_rows;
+    double wsum = 0.0;
+    for (int64_t b = threadIdx.x; b < nblocks; b += kMergeThreads) {
+        const int64_t rem = n_rows - b * rows_per_block;
+        const double nb = (double)(rem < rows_per_block ? rem : rows_per_block);
+        wsum += nb * partials[(b * ndims_in_partials + dim) * 2 + 0];
+    }
+    const double grand = block_sum_fixed(wsum, sm) / N;
+    double m2 = 0.0;
+    for (int64_t b = threadIdx.x; b < nblocks; b += kMergeThreads) {
+        const int64_t rem = n_rows - b * rows_per_block;
+        const double nb = (double)(rem < rows_per_block ? rem : rows_per_block);
+        const double dm = partials[(b * ndims_in_partials + dim) * 2 + 0] - grand;
+        m2 += partials[(b * ndims_in_partials + dim) * 2 + 1] + nb * dm * dm;
+    }
+    m2 = block_sum_fixed(m2, sm);
     if (threadIdx.x == 0) {
-        if (obs_stats) obs_stats[0] += (double)n_rows;
-        if (ret_stats) ret_stats[0] += (double)n_rows;
+        Moments B = {N, grand, m2};
+        if (dim < obs_dim) { if (obs_stats) fold_into_running(obs_stats, obs_dim, dim, B, nullptr); }
+        else if (ret_stats) fold_into_running(ret_stats, 1, 0, B, ret_std_out);
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {                // every dimension has read the old counts: advance them
+            if (obs_stats) obs_stats[0] += N;
+            if (ret_stats) ret_stats[0] += N;
+            *ticket = 0u;
+        }
     }
 }
 
@@ -401,8 +536,10 @@ __global__ void env_observe_kernel(const SatEnvState st, float* __restrict__ obs
 constexpr int kNormRows = 128;
 
 __global__ void __launch_bounds__(kNormRows)
-norm_partial_kernel(const double* __restrict__ x, int64_t n, int dim, double* __restrict__ partials) {
+norm_partial_kernel(const double* __restrict__ x, int64_t n, int dim, double* __restrict__ partials,
+                    unsigned int* __restrict__ ticket) {
     __shared__ double tile[kNormRows * 32];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;
     const int64_t row0 = (int64_t)blockIdx.x * kNormRows;
     const int64_t rem = n - row0;
     const int rows = (int)(rem < kNormRows ? rem : kNormRows);
@@ -449,12 +586,12 @@ inline int launch_status() {
 extern "C" {
 
 int64_t sat_workspace_bytes(int64_t n) {
-    if (n <= 0) return 256;
+    if (n <= 0) return kWsHeader;
     int64_t nb_env = (n + kEnvsPerBlock - 1) / kEnvsPerBlock;
     int64_t nb_norm = (n + kNormRows - 1) / kNormRows;
     int64_t a = nb_env * kStatDims * 2 * (int64_t)sizeof(double);
     int64_t b = nb_norm * 32 * 2 * (int64_t)sizeof(double);
-    return (a > b ? a : b) + 256;
+    return ws_partials_offset(n) + (a > b ? a : b);
 }
 
 void sat_env_default_params(SatEnvParams* p) {
@@ -510,28 +647,46 @@ int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const in
     int rc = check_state(st);
     if (rc) return rc;
     if (!pa || !ea || !reward || !done || !p) return SAT_ERR_NULL;
-    if ((obs_stats || ret_stats) && !workspace) return SAT_ERR_NULL;
+    const bool want_stats = obs_stats || ret_stats;
+    if ((want_stats || p->mode == SAT_MODE_RK4) && !workspace) return SAT_ERR_NULL;
     if (p->mode != SAT_MODE_CW && p->mode != SAT_MODE_RK4) return SAT_ERR_MODE;
     if (p->action_dtype != SAT_ACT_F32 && p->action_dtype != SAT_ACT_F64) return SAT_ERR_MODE;
     if (p->flag != 0 && p->flag != 1) return SAT_ERR_MODE;
     if (p->mode == SAT_MODE_RK4 && p->substeps < 1) return SAT_ERR_SIZE;
+    if (workspace && ((uintptr_t)workspace & 15)) return SAT_ERR_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t nblocks = (st->n + kEnvsPerBlock - 1) / kEnvsPerBlock;
-    double* partials = (obs_stats || ret_stats) ? (double*)workspace : nullptr;
-#define SAT_LAUNCH(MODE, T)                                                                           \
-    env_step_kernel<MODE, T><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const T*)pa, (const T*)ea,    \
-        count_override, obs_f32, obs_f64, term_obs_f64, reward, done, partials, *p)
+    const int64_t n = st->n;
+    const int64_t nblocks = (n + kEnvsPerBlock - 1) / kEnvsPerBlock;
+    char* ws = (char*)workspace;
+    unsigned int* ticket = ws ? (unsigned int*)ws : nullptr;
+    double* dis_prev = ws ? (double*)(ws + ws_disprev_offset()) : nullptr;
+    double* partials = want_stats ? (double*)(ws + ws_partials_offset(n)) : nullptr;
     if (p->mode == SAT_MODE_CW) {
-        if (p->action_dtype == SAT_ACT_F32) SAT_LAUNCH(SAT_MODE_CW, float); else SAT_LAUNCH(SAT_MODE_CW, double);
+        // one fused kernel: the propagation is a 6x6 product
+        if (p->action_dtype == SAT_ACT_F32)
+            env_step_kernel<true, float><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
+                count_override, obs_f32, obs_f64, term_obs_f64, reward, done, nullptr, partials, ticket, *p);
+        else
+            env_step_kernel<true, double><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
+                count_override, obs_f32, obs_f64, term_obs_f64, reward, done, nullptr, partials, ticket, *p);
     } else {
-        if (p->action_dtype == SAT_ACT_F32) SAT_LAUNCH(SAT_MODE_RK4, float); else SAT_LAUNCH(SAT_MODE_RK4, double);
+        // kernel A (FP64-pipe bound, <= 72 registers, whole batch resident) then kernel B (register-heavy, divergent)
+        const int64_t fblocks = (2 * n + kFrontBlock - 1) / kFrontBlock;
+        if (p->action_dtype == SAT_ACT_F32) {
+            env_front_rk4_kernel<float><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea, dis_prev, *p);
+            env_step_kernel<false, float><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
+                count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
+        } else {
+            env_front_rk4_kernel<double><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea, dis_prev, *p);
+            env_step_kernel<false, double><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
+                count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
+        }
     }
-#undef SAT_LAUNCH
     rc = launch_status();
     if (rc) return rc;
     if (partials) {
-        stats_merge_kernel<<<1, 32 * kStatDims, 0, s>>>(partials, nblocks, st->n, kEnvsPerBlock, kStatDims,
-                                                       obs_stats, kObs, ret_stats, ret_std_out);
+        stats_merge_kernel<<<kStatDims, kMergeThreads, 0, s>>>(partials, nblocks, n, kEnvsPerBlock, kStatDims,
+                                                               obs_stats, kObs, ret_stats, ret_std_out, ticket);
         rc = launch_status();
     }
     return rc;
@@ -550,7 +705,7 @@ int64_t sat_env_step_host_bytes(int64_t n) {
     if (n <= 0) return 0;
     // pa | ea (fp32 [n][3] each) | obs fp32 [n][18] | reward fp64 [n] | done u8 [n], each 256-byte aligned
     auto al = [](int64_t b) { return (b + 255) / 256 * 256; };
-    return al(n * 12) * 2 + al(n * 72) + al(n * 8) + al(n);
+    return al(n * 12) * 2 + al(n * 72) + al(n * 8) + al(n) + sat_workspace_bytes(n);
 }
 
 int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* ea_host,
@@ -568,13 +723,14 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
     float* d_obs = (float*)(base + 2 * al(n * 12));
     double* d_rew = (double*)(base + 2 * al(n * 12) + al(n * 72));
     uint8_t* d_done = (uint8_t*)(base + 2 * al(n * 12) + al(n * 72) + al(n * 8));
+    void* d_ws = (void*)(base + 2 * al(n * 12) + al(n * 72) + al(n * 8) + al(n));
     cudaError_t ce;
     if ((ce = cudaMemcpyAsync(d_pa, pa_host, n * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)ce;
     if ((ce = cudaMemcpyAsync(d_ea, ea_host, n * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)ce;
     SatEnvParams q = *p;
     q.action_dtype = SAT_ACT_F32;
     rc = sat_env_step(st, d_pa, d_ea, nullptr, d_obs, nullptr, nullptr, d_rew, d_done, nullptr, nullptr, nullptr,
-                      nullptr, &q, stream);
+                      d_ws, &q, stream);
     if (rc) return rc;
     if ((ce = cudaMemcpyAsync(obs_host, d_obs, n * 72, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
     if ((ce = cudaMemcpyAsync(reward_host, d_rew, n * 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
@@ -592,10 +748,12 @@ int sat_norm_update(double* stats, const double* x, int64_t n, int dim, int upda
     int rc;
     if (update) {
         const int64_t nblocks = (n + kNormRows - 1) / kNormRows;
-        norm_partial_kernel<<<(unsigned)nblocks, kNormRows, 0, s>>>(x, n, dim, (double*)workspace);
+        char* ws = (char*)workspace;
+        double* partials = (double*)(ws + ws_partials_offset(n));
+        norm_partial_kernel<<<(unsigned)nblocks, kNormRows, 0, s>>>(x, n, dim, partials, (unsigned int*)ws);
         if ((rc = launch_status())) return rc;
-        stats_merge_kernel<<<1, 32 * dim, 0, s>>>((const double*)workspace, nblocks, n, kNormRows, dim,
-                                                  stats, dim, nullptr, nullptr);
+        stats_merge_kernel<<<dim, kMergeThreads, 0, s>>>(partials, nblocks, n, kNormRows, dim,
+                                                         stats, dim, nullptr, nullptr, (unsigned int*)ws);
         if ((rc = launch_status())) return rc;
     }
     if (x_out_f64 || x_out_f32) {

@@ -257,75 +257,30 @@ __device__ __noinline__ double hybrd1(const F& fcn, double x0) {
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// rf_extreme_point('orbit_c1' / 'orbit_c2'), satellite_function.py:462-556, with fai = 0 (:33).
-// f_cx is f_c1 or f_c2. Writes (rf_max, rf_min).
-// ------------------------------------------------------------------------------------------
-struct PursuerOrbit { double u, dv, e_c, f0_c, r_c, p_c; };
-
-SAT_DEV double rf_from_alpha(const PursuerOrbit& o, double sq_e_sin, double sq_k, double dvm, double alpha,
-                             double cth, double sth) {
-    double s, c;
-    sincos(alpha, &s, &c);
-    double v1x = sq_e_sin + dvm * c;                                      // :525 / :541
-    double v1y = sq_k + dvm * s;                                          // :526 / :542 (cos(beta) = 1 folded by caller)
-    double hm = o.r_c * v1y;
-    return (hm * hm) / (o.u * (1.0 - cth) + hm * v1y * cth - hm * v1x * sth);   // :530 / :545
-}
-
 struct DzDebug { double rf_max, rf_min, r_ft, alpha0, alpha1, theta, dvm, f_cx; };
 
-static __device__ __noinline__ void rf_extreme_point(const PursuerOrbit& o, double f_cx, double& rf_max, double& rf_min,
-                                                     DzDebug* dbg) {
-    double df = f_cx - o.f0_c;
-    double sdf, cdf;
-    sincos(df, &sdf, &cdf);
-    double k = 1.0 + o.e_c * cos(o.f0_c);
-    double temp1 = (sdf * sdf) / (o.u * (k * k) / (o.p_c * (o.dv * o.dv)) - 1.0);     // :466 / :481
-    if (dbg) { dbg->alpha0 = 0.0; dbg->alpha1 = 0.0; dbg->theta = 0.0; dbg->dvm = 0.0; }
-    if (!(0.0 <= temp1)) { rf_max = 0.0; rf_min = 0.0; return; }                      // :478
-    double beta = atan(0.0 / sdf);                                                    // :469, tan(fai) = 0
-    double sb = sin(beta), cb = cos(beta);
-    double dvm = sqrt(o.dv * o.dv - o.u * (k * k) * (sb * sb) / o.p_c);               // :470
-    double theta = 0.0;                                                               // :464 (stays 0 outside both ranges, Q5)
-    if ((-kTwoPi <= df && df < -kPi) || (0.0 <= df && df < kPi)) theta = acos(cdf * 1.0);             // :473-474
-    else if ((-kPi <= df && df < 0.0) || (kPi <= df && df < kTwoPi)) theta = kTwoPi - acos(cdf * 1.0);  // :475-476
-    double sth, cth;
-    sincos(theta, &sth, &cth);
-    double sq = sqrt(o.u / o.p_c);
-    double sq_e_sin = sq * o.e_c * sin(o.f0_c);                                       // :518 first term
-    double sq_k = sq * (1.0 + o.e_c * cos(o.f0_c)) * cb;                              // :519 first term
-    double r[2];
-#pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
-        double ag = (j == 0) ? kPi / 2 : -kPi / 2;                                    // :516 / :534
-        double sg, cg;
-        sincos(ag, &sg, &cg);
-        double v1x = sq_e_sin + dvm * cg;
-        double v1y = sq_k + dvm * sg;
-        double h = o.r_c * v1y;                                                       // :521
-        PFai f;
-        f.A = (2.0 * o.u * (1.0 - cth)) / (h * v1y) - v1x * sth / v1y;                // :560
-        f.sth = sth; f.dvm = dvm;
-        double alpha = hybrd1(f, ag);                                                 // :523 / :540
-        r[j] = fabs(rf_from_alpha(o, sq_e_sin, sq_k, dvm, alpha, cth, sth));          // :549-550
-        if (dbg) { if (j == 0) dbg->alpha0 = alpha; else dbg->alpha1 = alpha; }
-    }
-    if (dbg) { dbg->theta = theta; dbg->dvm = dvm; }
-    if (r[0] < r[1]) { rf_max = r[1]; rf_min = r[0]; } else { rf_max = r[0]; rf_min = r[1]; }   // :551-554
-}
-
-
 // ------------------------------------------------------------------------------------------
-// danger-zone count for one environment evaluated by a LANE PAIR (even lane = pursuer "c", odd lane =
-// target "t"): environment.py:317-332 -> satellite_function.py:18-99, 317-373. Each lane converts its own
-// craft to orbital elements, the pair swaps them with shfl.xor 1, and each lane then solves one of the two
-// relative-node reachability problems (lane 0: node 1, lane 1: node 2). MUST be called by all 32 lanes of
-// the warp (the shuffles are warp-wide); `active` predicates the work.
-// Returns 0/1/2, or -1 when the reference would raise (circular / parabolic element set).
+// Danger-zone count for one environment, evaluated by a LANE PAIR in three phases so that the expensive,
+// data-dependent part (the fsolve iterations) can be compacted across the CTA:
+//   dz_prepare  : each lane converts its own craft to orbital elements, the pair swaps them with shfl.xor 1,
+//                 and each lane sets up ONE relative node (lane 0: node 1, lane 1: node 2): reachability test,
+//                 theta, dVm and the two frozen-coefficient root problems (alpha_guess = +pi/2, -pi/2)
+//   solve tasks : alpha = hybrd1(PFai{A, sth, dvm}, guess) -- independent work items; the kernels push them
+//                 into a shared-memory queue and run them densely packed (only ~1/4 of the lanes have any)
+//   dz_finalize : rf extremes from the two roots, interval test, pair sum -> 0/1/2
+// environment.py:317-332 -> satellite_function.py:18-99, 317-373, 462-556. dz_prepare and dz_finalize contain
+// warp-wide shuffles and MUST be called by all 32 lanes; `active` predicates the work.
 // ------------------------------------------------------------------------------------------
-SAT_DEV int danger_zone_pair(int craft, bool active, const double Ri[3], const double Vi[3], double fuel_c,
-                             double u_grav, DzDebug* dbg) {
+struct DzNode {
+    // state of one node's reachability problem between the phases
+    double u, r_c, sq_e_sin, sq_k, dvm, sth, cth, r_ft;
+    double A0, A1;          // P_fai coefficient for the +pi/2 and -pi/2 guesses (frozen at the guess, :518-523)
+    int status;             // -1: element set for which the reference raises; 0: inactive; 1: unreachable (rf = 0,0); 2: two solves
+    double theta, f_cx;     // diagnostics
+};
+
+SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double Vi[3], double fuel_c,
+                        double u_grav, DzNode& nd) {
     Elements el_own = {0, 0, 0, 0, 0, 0};
     int ok = 0;
     if (active) ok = orbital_elements(u_grav, Ri, Vi, el_own) ? 1 : 0;
@@ -334,36 +289,101 @@ SAT_DEV int danger_zone_pair(int craft, bool active, const double Ri[3], const d
     el_oth.i = __shfl_xor_sync(0xffffffffu, el_own.i, 1); el_oth.omega = __shfl_xor_sync(0xffffffffu, el_own.omega, 1);
     el_oth.Omega = __shfl_xor_sync(0xffffffffu, el_own.Omega, 1); el_oth.f = __shfl_xor_sync(0xffffffffu, el_own.f, 1);
     const int ok_both = ok & __shfl_xor_sync(0xffffffffu, ok, 1);
+    nd.status = 0; nd.dvm = 0.0; nd.theta = 0.0; nd.f_cx = 0.0; nd.r_ft = 0.0;
+    nd.A0 = 0.0; nd.A1 = 0.0; nd.sth = 0.0; nd.cth = 1.0; nd.sq_e_sin = 0.0; nd.sq_k = 0.0; nd.r_c = 0.0; nd.u = u_grav;
+    if (!active) return;
+    if (!ok_both) { nd.status = -1; return; }
+    const Elements& c = craft == 0 ? el_own : el_oth;     // pursuer
+    const Elements& t = craft == 0 ? el_oth : el_own;     // target
+    // calculate_latitudinal_angle, satellite_function.py:326-337
+    double si_t, ci_t, si_c, ci_c, sdo, cdo, sdo2, cdo2;
+    sincos(t.i, &si_t, &ci_t); sincos(c.i, &si_c, &ci_c);
+    sincos(c.Omega - t.Omega, &sdo, &cdo);
+    sincos(t.Omega - c.Omega, &sdo2, &cdo2);
+    double temp1 = (si_t * sdo) / (ci_t * si_c - si_t * ci_c * cdo);
+    double temp2 = (si_c * sdo2) / (ci_c * si_t - si_c * ci_t * cdo2);
+    if (isnan(temp1) || isnan(temp2)) { temp1 = 1.0; temp2 = 1.0; }      // :331-332
+    const double u_c1 = atan(temp1), u_t1 = atan(temp2);
+    // :352-355; lane 0 -> node 1 (f_c1, r_ft1 uses f_t2), lane 1 -> node 2 (f_c2, r_ft2 uses f_t1) (Q5)
+    const double f_cx = (craft == 0 ? u_c1 : kPi + u_c1) - c.omega;
+    const double f_tx = (craft == 0 ? u_t1 + kPi : u_t1) - t.omega;
+    nd.f_cx = f_cx;
+    nd.r_ft = (t.a * (1.0 - t.e * t.e)) / (1.0 + t.e * cos(f_tx));       // :363 / :365
+    const double one_m_e2 = 1.0 - c.e * c.e;
+    double sf0, cf0;
+    sincos(c.f, &sf0, &cf0);
+    const double k = 1.0 + c.e * cf0;
+    const double r_c = c.a * one_m_e2 / k;                                // :57
+    const double p_c = c.a * one_m_e2;                                    // :58
+    const double dv = fuel_c;                                             // Delta_V_c (:328)
+    // rf_extreme_point, satellite_function.py:462-494 with fai = 0
+    const double df = f_cx - c.f;
+    double sdf, cdf;
+    sincos(df, &sdf, &cdf);
+    const double tmp1 = (sdf * sdf) / (u_grav * (k * k) / (p_c * (dv * dv)) - 1.0);   // :466 / :481
+    if (!(0.0 <= tmp1)) { nd.status = 1; return; }                                    // :478 -> (0, 0)
+    const double beta = atan(0.0 / sdf);                                              // :469, tan(fai) = 0
+    double sb, cb;
+    sincos(beta, &sb, &cb);
+    const double dvm = sqrt(dv * dv - u_grav * (k * k) * (sb * sb) / p_c);            // :470
+    double theta = 0.0;                                                               // :464 (stays 0 outside both ranges, Q5)
+    if ((-kTwoPi <= df && df < -kPi) || (0.0 <= df && df < kPi)) theta = acos(cdf * 1.0);             // :473-474
+    else if ((-kPi <= df && df < 0.0) || (kPi <= df && df < kTwoPi)) theta = kTwoPi - acos(cdf * 1.0);  // :475-476
+    double sth, cth;
+    sincos(theta, &sth, &cth);
+    const double sq = sqrt(u_grav / p_c);
+    const double sq_e_sin = sq * c.e * sf0;                                           // :518 first term
+    const double sq_k = sq * k * cb;                                                  // :519 first term
+    nd.r_c = r_c; nd.sq_e_sin = sq_e_sin; nd.sq_k = sq_k; nd.dvm = dvm; nd.sth = sth; nd.cth = cth; nd.theta = theta;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const double ag = (j == 0) ? kPi / 2 : -kPi / 2;                              // :516 / :534
+        double sg, cg;
+        sincos(ag, &sg, &cg);
+        const double v1x = sq_e_sin + dvm * cg;
+        const double v1y = sq_k + dvm * sg;
+        const double h = r_c * v1y;                                                   // :521
+        const double A = (2.0 * u_grav * (1.0 - cth)) / (h * v1y) - v1x * sth / v1y;  // :560
+        if (j == 0) nd.A0 = A; else nd.A1 = A;
+    }
+    nd.status = 2;
+}
+
+// one queued root problem: satellite_function.py:523 / :540 -> :558-565
+SAT_DEV double dz_solve(double A, double sth, double dvm, int j) {
+    PFai f;
+    f.A = A; f.sth = sth; f.dvm = dvm;
+    return hybrd1(f, (j == 0) ? kPi / 2 : -kPi / 2);
+}
+
+SAT_DEV double dz_rf(const DzNode& nd, double alpha) {
+    double s, c;
+    sincos(alpha, &s, &c);
+    const double v1x = nd.sq_e_sin + nd.dvm * c;                                      // :525 / :541
+    const double v1y = nd.sq_k + nd.dvm * s;                                          // :526 / :542
+    const double hm = nd.r_c * v1y;
+    return fabs((hm * hm) / (nd.u * (1.0 - nd.cth) + hm * v1y * nd.cth - hm * v1x * nd.sth));   // :530 / :545, :549-550
+}
+
+// returns 0/1/2, or -1 when the reference would raise; alpha0/alpha1 are ignored unless nd.status == 2
+SAT_DEV int dz_finalize(bool active, const DzNode& nd, double alpha0, double alpha1, DzDebug* dbg) {
     int inside = 0;
-    if (active && ok_both) {
-        const Elements& c = craft == 0 ? el_own : el_oth;     // pursuer
-        const Elements& t = craft == 0 ? el_oth : el_own;     // target
-        // calculate_latitudinal_angle, satellite_function.py:326-337
-        double si_t, ci_t, si_c, ci_c, sdo, cdo, sdo2, cdo2;
-        sincos(t.i, &si_t, &ci_t); sincos(c.i, &si_c, &ci_c);
-        sincos(c.Omega - t.Omega, &sdo, &cdo);
-        sincos(t.Omega - c.Omega, &sdo2, &cdo2);
-        double temp1 = (si_t * sdo) / (ci_t * si_c - si_t * ci_c * cdo);
-        double temp2 = (si_c * sdo2) / (ci_c * si_t - si_c * ci_t * cdo2);
-        if (isnan(temp1) || isnan(temp2)) { temp1 = 1.0; temp2 = 1.0; }      // :331-332
-        const double u_c1 = atan(temp1), u_t1 = atan(temp2);
-        // :352-355; lane 0 -> node 1 (f_c1, r_ft1 uses f_t2), lane 1 -> node 2 (f_c2, r_ft2 uses f_t1) (Q5)
-        const double f_cx = (craft == 0 ? u_c1 : kPi + u_c1) - c.omega;
-        const double f_tx = (craft == 0 ? u_t1 + kPi : u_t1) - t.omega;
-        PursuerOrbit o;
-        o.u = u_grav; o.dv = fuel_c; o.e_c = c.e; o.f0_c = c.f;
-        const double one_m_e2 = 1.0 - c.e * c.e;
-        o.r_c = c.a * one_m_e2 / (1.0 + c.e * cos(c.f));                      // :57
-        o.p_c = c.a * one_m_e2;                                               // :58
-        double rf_max, rf_min;
-        rf_extreme_point(o, f_cx, rf_max, rf_min, dbg);                       // :359 / :361
-        const double r_ft = (t.a * (1.0 - t.e * t.e)) / (1.0 + t.e * cos(f_tx));   // :363 / :365
-        inside = (rf_min <= r_ft && r_ft <= rf_max) ? 1 : 0;                  // :367-372
-        if (dbg) { dbg->rf_max = rf_max; dbg->rf_min = rf_min; dbg->r_ft = r_ft; dbg->f_cx = f_cx; }
+    double rf_max = 0.0, rf_min = 0.0;
+    if (nd.status == 2) {
+        const double r0 = dz_rf(nd, alpha0), r1 = dz_rf(nd, alpha1);
+        if (r0 < r1) { rf_max = r1; rf_min = r0; } else { rf_max = r0; rf_min = r1; }    // :551-554
+    }
+    if (nd.status >= 1) inside = (rf_min <= nd.r_ft && nd.r_ft <= rf_max) ? 1 : 0;        // :367-372
+    if (dbg) {
+        dbg->rf_max = rf_max; dbg->rf_min = rf_min; dbg->r_ft = nd.r_ft; dbg->f_cx = nd.f_cx;
+        dbg->alpha0 = nd.status == 2 ? alpha0 : 0.0; dbg->alpha1 = nd.status == 2 ? alpha1 : 0.0;
+        dbg->theta = nd.theta; dbg->dvm = nd.dvm;
     }
     const int inside_sum = inside + __shfl_xor_sync(0xffffffffu, inside, 1);
+    const int bad = (nd.status < 0) ? 1 : 0;
+    const int bad_any = bad | __shfl_xor_sync(0xffffffffu, bad, 1);
     if (!active) return 0;
-    return ok_both ? inside_sum : -1;
+    return bad_any ? -1 : inside_sum;
 }
 
 // ------------------------------------------------------------------------------------------

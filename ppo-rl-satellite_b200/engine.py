@@ -400,9 +400,11 @@ def adv_normalize_(adv, sums=None, group=None):
     torch = L.require_cuda()
     if sums is None:
         sums = adv_moments(adv)
-    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                             and torch.distributed.get_world_size() > 1 and group is not False):
-        torch.distributed.all_reduce(sums, group=group if group not in (None, True) else None)
+    dist = torch.distributed
+    if group is not False and dist.is_available() and dist.is_initialized():
+        pg = None if group in (None, True) else group
+        if dist.get_world_size(pg) > 1:
+            dist.all_reduce(sums, group=pg)
     flat = adv.reshape(-1)
     L.check(L.load().sat_adv_normalize(L.ptr(flat), flat.numel(), L.ptr(sums), L.stream_ptr()), "sat_adv_normalize")
     return adv
