@@ -148,36 +148,49 @@ env_front_rk4_kernel(const SatEnvState st, const ActT* __restrict__ pa, const Ac
 // ---------------------------------------------------------------------------------------------
 struct SolveQueue {
     double A[2 * kBlock], sth[2 * kBlock], dvm[2 * kBlock], alpha[2 * kBlock];
-    int warp_count[kBlock / 32];
+    int guess[2 * kBlock];
+    int count, next;
 };
 
-SAT_DEV int queue_push(SolveQueue& q, const DzNode& nd) {
-    // returns this lane's first task index (tasks idx, idx+1), or -1; contains __syncthreads
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool has = nd.status == 2;
-    const unsigned m = __ballot_sync(0xffffffffu, has);
-    if (lane == 0) q.warp_count[warp] = __popc(m);
+SAT_DEV void queue_init(SolveQueue& q) {
+    if (threadIdx.x == 0) { q.count = 0; q.next = 0; }
     __syncthreads();
-    int base = 0;
-#pragma unroll
-    for (int w = 0; w < kBlock / 32; ++w) base += (w < warp) ? q.warp_count[w] : 0;
-    int idx = -1;
-    if (has) {
-        idx = 2 * (base + __popc(m & ((1u << lane) - 1u)));
-        q.A[idx] = nd.A0; q.A[idx + 1] = nd.A1;
-        q.sth[idx] = nd.sth; q.sth[idx + 1] = nd.sth;
-        q.dvm[idx] = nd.dvm; q.dvm[idx + 1] = nd.dvm;
-    }
-    __syncthreads();
-    return idx;
 }
 
+// pushes the lane's non-degenerate root problems; returns their slots (-1: none / solved in place)
+SAT_DEV void queue_push(SolveQueue& q, const DzNode& nd, int& slot0, int& slot1, double& alpha0, double& alpha1) {
+    slot0 = -1; slot1 = -1; alpha0 = dz_guess(0); alpha1 = dz_guess(1);
+    if (nd.status == 2) {
+        const bool g0 = dz_degenerate(nd.A0, nd.sth, nd.dvm), g1 = dz_degenerate(nd.A1, nd.sth, nd.dvm);
+        const int cnt = (g0 ? 0 : 1) + (g1 ? 0 : 1);
+        if (cnt) {
+            int s = atomicAdd(&q.count, cnt);
+            if (!g0) { slot0 = s; q.A[s] = nd.A0; q.sth[s] = nd.sth; q.dvm[s] = nd.dvm; q.guess[s] = 0; ++s; }
+            if (!g1) { slot1 = s; q.A[s] = nd.A1; q.sth[s] = nd.sth; q.dvm[s] = nd.dvm; q.guess[s] = 1; }
+        }
+    }
+    __syncthreads();
+}
+
+// persistent lanes: every lane pulls the next root problem as soon as it finishes one, and all lanes of a warp
+// advance their own solver by one function evaluation per loop trip (uniform loop body, no per-task divergence)
 SAT_DEV void queue_run(SolveQueue& q) {
-    int total = 0;
-#pragma unroll
-    for (int w = 0; w < kBlock / 32; ++w) total += q.warp_count[w];
-    total *= 2;
-    for (int t = threadIdx.x; t < total; t += kBlock) q.alpha[t] = dz_solve(q.A[t], q.sth[t], q.dvm[t], t & 1);
+    const int total = q.count;
+    int task = -1;
+    Hybrd1<PFai> hs;
+    for (;;) {
+        if (task < 0) {
+            const int t = atomicAdd(&q.next, 1);
+            if (t < total) {
+                task = t;
+                PFai f; f.A = q.A[t]; f.sth = q.sth[t]; f.dvm = q.dvm[t];
+                hs.init(f, dz_guess(q.guess[t]));
+            } else task = total;                     // queue drained for this lane
+        }
+        const bool active = task < total;
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active && hs.step()) { q.alpha[task] = hs.x; task = -1; }
+    }
     __syncthreads();
 }
 
@@ -197,6 +210,7 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     __shared__ double tile[kEnvsPerBlock][kStatDims];        // next observation (+ return) of the CTA's envs
     __shared__ double tile_term[kEnvsPerBlock][kObs];        // pre-reset observation
     __shared__ SolveQueue queue;
+    queue_init(queue);
 
     const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const int64_t env_raw = tid >> 1;
@@ -247,9 +261,12 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
         for (int k = 0; k < 3; ++k) { Ri[k] = __dadd_rn(p.r_cw[k], L.r[k]); Vi[k] = __dadd_rn(p.v_cw[k], L.v[k]); }   // :338-341
         dz_prepare(craft, need_dz, Ri, Vi, fuel_c, p.u_grav, nd);
     }
-    const int qidx = queue_push(queue, nd);
+    int slot0, slot1;
+    double alpha0, alpha1;
+    queue_push(queue, nd, slot0, slot1, alpha0, alpha1);
     queue_run(queue);
-    const double alpha0 = qidx >= 0 ? queue.alpha[qidx] : 0.0, alpha1 = qidx >= 0 ? queue.alpha[qidx + 1] : 0.0;
+    if (slot0 >= 0) alpha0 = queue.alpha[slot0];
+    if (slot1 >= 0) alpha1 = queue.alpha[slot1];
     const int dz_eval = dz_finalize(need_dz, nd, alpha0, alpha1, nullptr);
     int dz_new = dz_stale;                                   // not refreshed on capture / time-out steps (Q3)
     if (need_dz) {
@@ -367,6 +384,7 @@ __global__ void __launch_bounds__(kBlock)
 danger_zone_kernel(const double* __restrict__ rv, const double* __restrict__ dv, int64_t n, double u_grav,
                    int32_t* __restrict__ count_out, double* __restrict__ debug_out) {
     __shared__ SolveQueue queue;
+    queue_init(queue);
     const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const int64_t env_raw = tid >> 1;
     const int craft = (int)(tid & 1);
@@ -377,9 +395,12 @@ danger_zone_kernel(const double* __restrict__ rv, const double* __restrict__ dv,
     for (int k = 0; k < 3; ++k) { Ri[k] = rv[e * 12 + craft * 6 + k]; Vi[k] = rv[e * 12 + craft * 6 + 3 + k]; }
     DzNode nd;
     dz_prepare(craft, true, Ri, Vi, dv[e], u_grav, nd);
-    const int qidx = queue_push(queue, nd);
+    int slot0, slot1;
+    double alpha0, alpha1;
+    queue_push(queue, nd, slot0, slot1, alpha0, alpha1);
     queue_run(queue);
-    const double alpha0 = qidx >= 0 ? queue.alpha[qidx] : 0.0, alpha1 = qidx >= 0 ? queue.alpha[qidx + 1] : 0.0;
+    if (slot0 >= 0) alpha0 = queue.alpha[slot0];
+    if (slot1 >= 0) alpha1 = queue.alpha[slot1];
     DzDebug dbg = {0, 0, 0, 0, 0, 0, 0, 0};
     const int dz = dz_finalize(true, nd, alpha0, alpha1, debug_out ? &dbg : nullptr);
     if (valid) {

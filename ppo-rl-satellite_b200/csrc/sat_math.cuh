@@ -186,75 +186,112 @@ struct PFai {
     }
 };
 
+// The iteration is written as a state machine with ONE function-evaluation site per step(): lanes of a
+// warp that are in different phases (initial value / forward-difference Jacobian / trial point) or even on
+// different root problems still execute the expensive sincos together. The arithmetic and its order are
+// exactly MINPACK's (Appendix B), so the iterates are bit-identical to the straight-line form.
 template <class F>
-__device__ __noinline__ double hybrd1(const F& fcn, double x0) {
-    const double epsmch = 2.220446049250313e-16, xtol = 1.49012e-08, factor = 100.0;
-    const double sqeps = 1.4901161193847656e-08;   // sqrt(epsmch), exact power of two
-    const int maxfev = 400;
-    double x = x0, fv = fcn(x), fnorm = fabs(fv), d = 0.0, delta = 0.0, xnorm = 0.0;
-    int nfev = 1, iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
-    for (;;) {
-        bool jeval = true;
-        double h = sqeps * fabs(x);
-        if (h == 0.0) h = sqeps;
-        double a = (fcn(x + h) - fv) / h; ++nfev;
-        double r = -a, q = (a != 0.0) ? -1.0 : 1.0;
-        if (iter == 1) {
-            d = (fabs(a) != 0.0) ? fabs(a) : 1.0;
-            xnorm = fabs(d * x);
-            delta = factor * xnorm;
-            if (delta == 0.0) delta = factor;
-        }
-        double qtf = q * fv;
-        d = fmax(d, fabs(a));
-        for (;;) {
-            double t = r;
-            if (t == 0.0) { t = epsmch * fabs(r); if (t == 0.0) t = epsmch; }
-            double xgn = qtf / t, qnorm = fabs(d * xgn), step;
-            if (qnorm <= delta) step = xgn;
-            else {
-                double w = (r * qtf) / d, gnorm = fabs(w), sgnorm = 0.0, alpha = delta / qnorm;
-                if (gnorm != 0.0) {
-                    w = (w / gnorm) / d;
-                    double tt = fabs(r * w);
-                    sgnorm = (gnorm / tt) / tt; alpha = 0.0;
-                    if (sgnorm < delta) {
-                        double bnorm = fabs(qtf), dq = delta / qnorm, sd = sgnorm / delta;
-                        double tmp = (bnorm / gnorm) * (bnorm / qnorm) * sd;
-                        tmp = tmp - dq * sd * sd + sqrt((tmp - dq) * (tmp - dq) + (1.0 - dq * dq) * (1.0 - sd * sd));
-                        alpha = (dq * (1.0 - sd * sd)) / tmp;
-                    }
-                }
-                step = (1.0 - alpha) * fmin(sgnorm, delta) * w + alpha * xgn;
-            }
-            double p = -step, xt = x + p, pnorm = fabs(d * p);
-            if (iter == 1) delta = fmin(delta, pnorm);
-            double ft = fcn(xt); ++nfev;
-            double fnorm1 = fabs(ft);
-            double actred = (fnorm1 < fnorm) ? 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm) : -1.0;
-            double pred = qtf + r * p;
-            double prered = (fabs(pred) < fnorm) ? 1.0 - (fabs(pred) / fnorm) * (fabs(pred) / fnorm) : 0.0;
-            double ratio = (prered > 0.0) ? actred / prered : 0.0;
-            if (ratio < 0.1) { ncsuc = 0; ++ncfail; delta = 0.5 * delta; }
-            else {
-                ncfail = 0; ++ncsuc;
-                if (ratio >= 0.5 || ncsuc > 1) delta = fmax(delta, pnorm / 0.5);
-                if (fabs(ratio - 1.0) <= 0.1) delta = pnorm / 0.5;
-            }
-            if (ratio >= 1e-4) { x = xt; fv = ft; xnorm = fabs(d * x); fnorm = fnorm1; ++iter; }
-            ++nslow1; if (actred >= 1e-3) nslow1 = 0;
-            if (jeval) ++nslow2;
-            if (actred >= 0.1) nslow2 = 0;
-            if (delta <= xtol * xnorm || fnorm == 0.0) return x;               // info 1
-            if (nfev >= maxfev) return x;                                      // info 2
-            if (0.1 * fmax(0.1 * delta, pnorm) <= epsmch * xnorm) return x;    // info 3
-            if (nslow2 == 5 || nslow1 == 10) return x;                         // info 4 / 5
-            if (ncfail == 2) break;
-            double s = q * ft, v = (s - pred) / pnorm, uu = d * ((d * p) / pnorm);
-            if (ratio >= 1e-4) qtf = s;
-            r = r + uu * v; jeval = false;
-        }
+struct Hybrd1 {
+    F f;
+    double x, fv, fnorm, d, delta, xnorm, r, q, qtf, h, xt, p, pnorm;
+    int nfev, iter, ncsuc, ncfail, nslow1, nslow2, phase;   // phase 0: f(x0), 1: f(x+h) (Jacobian), 2: f(xt) (trial)
+    bool jeval;
+
+    SAT_DEV void init(const F& fn, double x0) {
+        f = fn; x = x0; fv = 0.0; fnorm = 0.0; d = 0.0; delta = 0.0; xnorm = 0.0; r = 0.0; q = 1.0; qtf = 0.0;
+        h = 0.0; xt = x0; p = 0.0; pnorm = 0.0;
+        nfev = 0; iter = 1; ncsuc = 0; ncfail = 0; nslow1 = 0; nslow2 = 0; phase = 0; jeval = true;
     }
+    SAT_DEV void start_outer() {
+        const double sqeps = 1.4901161193847656e-08;          // sqrt(machine eps), exact power of two
+        h = sqeps * fabs(x);
+        if (h == 0.0) h = sqeps;
+        phase = 1;
+    }
+    SAT_DEV void dogleg() {
+        const double epsmch = 2.220446049250313e-16;
+        double t = r;
+        if (t == 0.0) { t = epsmch * fabs(r); if (t == 0.0) t = epsmch; }
+        const double xgn = qtf / t, qnorm = fabs(d * xgn);
+        double step;
+        if (qnorm <= delta) step = xgn;
+        else {
+            double w = (r * qtf) / d, gnorm = fabs(w), sgnorm = 0.0, alpha = delta / qnorm;
+            if (gnorm != 0.0) {
+                w = (w / gnorm) / d;
+                const double tt = fabs(r * w);
+                sgnorm = (gnorm / tt) / tt; alpha = 0.0;
+                if (sgnorm < delta) {
+                    const double bnorm = fabs(qtf), dq = delta / qnorm, sd = sgnorm / delta;
+                    double tmp = (bnorm / gnorm) * (bnorm / qnorm) * sd;
+                    tmp = tmp - dq * sd * sd + sqrt((tmp - dq) * (tmp - dq) + (1.0 - dq * dq) * (1.0 - sd * sd));
+                    alpha = (dq * (1.0 - sd * sd)) / tmp;
+                }
+            }
+            step = (1.0 - alpha) * fmin(sgnorm, delta) * w + alpha * xgn;
+        }
+        p = -step; xt = x + p; pnorm = fabs(d * p);
+        if (iter == 1) delta = fmin(delta, pnorm);
+        phase = 2;
+    }
+    // one function evaluation + bookkeeping; returns true when finished (root estimate in x)
+    SAT_DEV bool step() {
+        const double epsmch = 2.220446049250313e-16, xtol = 1.49012e-08, factor = 100.0;
+        const int maxfev = 400;
+        const double xe = (phase == 0) ? x : ((phase == 1) ? x + h : xt);
+        const double fe = f(xe);
+        ++nfev;
+        if (phase == 0) { fv = fe; fnorm = fabs(fv); start_outer(); return false; }
+        if (phase == 1) {
+            const double a = (fe - fv) / h;
+            r = -a; q = (a != 0.0) ? -1.0 : 1.0;
+            if (iter == 1) {
+                d = (fabs(a) != 0.0) ? fabs(a) : 1.0;
+                xnorm = fabs(d * x);
+                delta = factor * xnorm;
+                if (delta == 0.0) delta = factor;
+            }
+            qtf = q * fv;
+            d = fmax(d, fabs(a));
+            jeval = true;
+            dogleg();
+            return false;
+        }
+        const double ft = fe;
+        const double fnorm1 = fabs(ft);
+        const double actred = (fnorm1 < fnorm) ? 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm) : -1.0;
+        const double pred = qtf + r * p;
+        const double prered = (fabs(pred) < fnorm) ? 1.0 - (fabs(pred) / fnorm) * (fabs(pred) / fnorm) : 0.0;
+        const double ratio = (prered > 0.0) ? actred / prered : 0.0;
+        if (ratio < 0.1) { ncsuc = 0; ++ncfail; delta = 0.5 * delta; }
+        else {
+            ncfail = 0; ++ncsuc;
+            if (ratio >= 0.5 || ncsuc > 1) delta = fmax(delta, pnorm / 0.5);
+            if (fabs(ratio - 1.0) <= 0.1) delta = pnorm / 0.5;
+        }
+        if (ratio >= 1e-4) { x = xt; fv = ft; xnorm = fabs(d * x); fnorm = fnorm1; ++iter; }
+        ++nslow1; if (actred >= 1e-3) nslow1 = 0;
+        if (jeval) ++nslow2;
+        if (actred >= 0.1) nslow2 = 0;
+        if (delta <= xtol * xnorm || fnorm == 0.0) return true;               // info 1
+        if (nfev >= maxfev) return true;                                      // info 2
+        if (0.1 * fmax(0.1 * delta, pnorm) <= epsmch * xnorm) return true;    // info 3
+        if (nslow2 == 5 || nslow1 == 10) return true;                         // info 4 / 5
+        if (ncfail == 2) { start_outer(); return false; }                     // re-evaluate the Jacobian
+        const double s = q * ft, v = (s - pred) / pnorm, uu = d * ((d * p) / pnorm);   // Broyden rank-1 update
+        if (ratio >= 1e-4) qtf = s;
+        r = r + uu * v; jeval = false;
+        dogleg();
+        return false;
+    }
+};
+
+template <class F>
+SAT_DEV double hybrd1(const F& fcn, double x0) {
+    Hybrd1<F> s;
+    s.init(fcn, x0);
+    while (!s.step()) {}
+    return s.x;
 }
 
 struct DzDebug { double rf_max, rf_min, r_ft, alpha0, alpha1, theta, dvm, f_cx; };
@@ -349,12 +386,11 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     nd.status = 2;
 }
 
-// one queued root problem: satellite_function.py:523 / :540 -> :558-565
-SAT_DEV double dz_solve(double A, double sth, double dvm, int j) {
-    PFai f;
-    f.A = A; f.sth = sth; f.dvm = dvm;
-    return hybrd1(f, (j == 0) ? kPi / 2 : -kPi / 2);
-}
+// one root problem: satellite_function.py:523 / :540 -> :558-565
+SAT_DEV double dz_guess(int j) { return (j == 0) ? kPi / 2 : -kPi / 2; }
+// theta == 0 (Q5) makes P_fai identically zero: fsolve returns its initial guess unchanged after 3
+// evaluations (|f| == 0 exit). Exact shortcut; 45 % of the solves on env-visited states.
+SAT_DEV bool dz_degenerate(double A, double sth, double dvm) { return A == 0.0 && sth == 0.0 && fabs(dvm) <= 1.7976931348623157e308; }
 
 SAT_DEV double dz_rf(const DzNode& nd, double alpha) {
     double s, c;
