@@ -197,6 +197,20 @@ int sat_adv_moments(const float* adv, int64_t count, double* sums /*[3] device*/
 int sat_adv_normalize(float* adv, int64_t count, const double* sums /*[3] device*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Batched forms of the satellite_function.py / RK4-script helpers the drop-in facade exposes.
+ * ------------------------------------------------------------------------------------------------ */
+/* StateEq(t, RV) ("轨道外推-龙格库塔算法.py":15-30): f [6][ld] = [v, a(x)] for n states x [6][ld]. */
+int sat_state_eq(const double* x, double* f, int64_t n, int64_t ld, double mu, double re, double j2, void* stream);
+/* Clohessy_Wiltshire(...).State_transition_matrix(t) (satellite_function.py:753-781): x [6][ld] <- M x with
+ * numpy's dgemv summation order; stm_host is the row-major 6x6 matrix in HOST memory (copied into the launch). */
+int sat_cw_propagate(double* x, int64_t n, int64_t ld, const double* stm_host, void* stream);
+/* calculate_orbital_elements(miu, R0, V0) (satellite_function.py:161-255): rv [n][6] -> (a,e,i,omega,Omega,f) [n][6];
+ * kind_out [n] = 6, or 0 for the circular / parabolic element sets (which this library does not produce). */
+int sat_orbital_elements(const double* rv, int64_t n, double miu, double* elements_out, int32_t* kind_out, void* stream);
+/* calculate_state_information(data, miu) (satellite_function.py:257-315), six-element form: -> rv [n][6]. */
+int sat_state_from_elements(const double* elements, int64_t n, double miu, double* rv_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): dependent-free DFMA / FFMA chains to measure the FP64 / FP32
  * vector peaks on the device the bench runs on (MEASURED_PEAKS.json has no such entries).
  * Each launches one kernel doing `iters` x 16 independent FMAs per thread; flops_out (host) receives

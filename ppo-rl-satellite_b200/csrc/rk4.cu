@@ -79,6 +79,69 @@ __global__ void peak_kernel(T* sink, int iters) {
     if (s == (T)-1.2345) sink[0] = s;     // never true; keeps the chains alive
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// helper kernels behind the satellite_function.py facade (batched forms of the reference helpers)
+// ------------------------------------------------------------------------------------------------
+// StateEq (script :15-30): f = [v, a(x)]
+template <bool J2>
+__global__ void state_eq_kernel(const double* __restrict__ x, double* __restrict__ f, int64_t n, int64_t ld,
+                                double mu, double re, double j2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ax, ay, az;
+    accel_scaled<J2>(x[i], x[ld + i], x[2 * ld + i], 1.5 * j2 * re * re, ax, ay, az);
+    f[i] = x[3 * ld + i]; f[ld + i] = x[4 * ld + i]; f[2 * ld + i] = x[5 * ld + i];
+    f[3 * ld + i] = -mu * ax; f[4 * ld + i] = -mu * ay; f[5 * ld + i] = -mu * az;
+}
+
+// Clohessy_Wiltshire.State_transition_matrix (satellite_function.py:753-781): x <- M x, numpy's dgemv order
+struct Stm36 { double m[36]; };
+__global__ void cw_apply_kernel(double* __restrict__ x, int64_t n, int64_t ld, const __grid_constant__ Stm36 M) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v[6], y[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = x[k * ld + i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) y[k] = gemv6_row(M.m + 6 * k, v);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k * ld + i] = y[k];
+}
+
+// calculate_orbital_elements (satellite_function.py:161-255), six-element branch
+__global__ void elements_kernel(const double* __restrict__ rv, int64_t n, double miu, double* __restrict__ out,
+                                int32_t* __restrict__ kind) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double R[3] = {rv[i * 6], rv[i * 6 + 1], rv[i * 6 + 2]}, V[3] = {rv[i * 6 + 3], rv[i * 6 + 4], rv[i * 6 + 5]};
+    Elements el = {0, 0, 0, 0, 0, 0};
+    const bool ok = orbital_elements(miu, R, V, el);
+    out[i * 6] = el.a; out[i * 6 + 1] = el.e; out[i * 6 + 2] = el.i;
+    out[i * 6 + 3] = el.omega; out[i * 6 + 4] = el.Omega; out[i * 6 + 5] = el.f;
+    kind[i] = ok ? 6 : 0;
+}
+
+// calculate_state_information (satellite_function.py:257-315), six-element form
+__global__ void state_info_kernel(const double* __restrict__ el, int64_t n, double miu, double* __restrict__ rv) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const double a = el[idx * 6], e = el[idx * 6 + 1], i = el[idx * 6 + 2], omega = el[idx * 6 + 3],
+                 Omega = el[idx * 6 + 4], f = el[idx * 6 + 5];
+    const double p = fabs(a * (1.0 - e * e));                 // :285
+    const double u = omega + f;                               // :286
+    double sO, cO, su, cu, si, ci, so, co;
+    sincos(Omega, &sO, &cO); sincos(u, &su, &cu); sincos(i, &si, &ci); sincos(omega, &so, &co);
+    const double k = p / (1.0 + e * cos(f));                  // :303
+    rv[idx * 6 + 0] = k * (cO * cu - sO * su * ci);
+    rv[idx * 6 + 1] = k * (sO * cu + cO * su * ci);
+    rv[idx * 6 + 2] = k * (si * su);
+    const double s = sqrt(miu / p);                           // :309
+    rv[idx * 6 + 3] = s * (-cO * (su + e * so) - sO * (cu + e * co) * ci);
+    rv[idx * 6 + 4] = s * (-sO * (su + e * so) + cO * (cu + e * co) * ci);
+    rv[idx * 6 + 5] = s * (si * (cu + e * co));
+}
+
 inline int launch_status() {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SAT_OK : (int)e;
@@ -123,6 +186,38 @@ int sat_rk4_propagate_host(double* x_host, int64_t n, double* d_scratch, int64_t
     if (ce != cudaSuccess) return (int)ce;
     ce = cudaStreamSynchronize(s);
     return ce == cudaSuccess ? SAT_OK : (int)ce;
+}
+
+int sat_state_eq(const double* x, double* f, int64_t n, int64_t ld, double mu, double re, double j2, void* stream) {
+    if (!x || !f) return SAT_ERR_NULL;
+    if (n <= 0 || ld < n) return SAT_ERR_SIZE;
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (j2 != 0.0) state_eq_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(x, f, n, ld, mu, re, j2);
+    else state_eq_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(x, f, n, ld, mu, re, j2);
+    return launch_status();
+}
+
+int sat_cw_propagate(double* x, int64_t n, int64_t ld, const double* stm_host, void* stream) {
+    if (!x || !stm_host) return SAT_ERR_NULL;
+    if (n <= 0 || ld < n) return SAT_ERR_SIZE;
+    Stm36 M;
+    for (int k = 0; k < 36; ++k) M.m[k] = stm_host[k];
+    cw_apply_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, n, ld, M);
+    return launch_status();
+}
+
+int sat_orbital_elements(const double* rv, int64_t n, double miu, double* elements_out, int32_t* kind_out, void* stream) {
+    if (!rv || !elements_out || !kind_out) return SAT_ERR_NULL;
+    if (n <= 0) return SAT_ERR_SIZE;
+    elements_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(rv, n, miu, elements_out, kind_out);
+    return launch_status();
+}
+
+int sat_state_from_elements(const double* elements, int64_t n, double miu, double* rv_out, void* stream) {
+    if (!elements || !rv_out) return SAT_ERR_NULL;
+    if (n <= 0) return SAT_ERR_SIZE;
+    state_info_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(elements, n, miu, rv_out);
+    return launch_status();
 }
 
 int sat_peak_fp64(double* sink, int blocks, int threads, int iters, double* flops_out_host, void* stream) {

@@ -234,15 +234,17 @@ struct Hybrd1 {
         if (iter == 1) delta = fmin(delta, pnorm);
         phase = 2;
     }
-    // one function evaluation + bookkeeping; returns true when finished (root estimate in x)
+    // one function evaluation + bookkeeping; returns true when finished (root estimate in x).
+    // Single evaluation site and single dogleg site: lanes in different phases share both.
     SAT_DEV bool step() {
         const double epsmch = 2.220446049250313e-16, xtol = 1.49012e-08, factor = 100.0;
         const int maxfev = 400;
         const double xe = (phase == 0) ? x : ((phase == 1) ? x + h : xt);
         const double fe = f(xe);
         ++nfev;
-        if (phase == 0) { fv = fe; fnorm = fabs(fv); start_outer(); return false; }
-        if (phase == 1) {
+        bool need_dogleg = false, finished = false;
+        if (phase == 0) { fv = fe; fnorm = fabs(fv); start_outer(); }
+        else if (phase == 1) {
             const double a = (fe - fv) / h;
             r = -a; q = (a != 0.0) ? -1.0 : 1.0;
             if (iter == 1) {
@@ -254,35 +256,38 @@ struct Hybrd1 {
             qtf = q * fv;
             d = fmax(d, fabs(a));
             jeval = true;
-            dogleg();
-            return false;
+            need_dogleg = true;
+        } else {
+            const double ft = fe;
+            const double fnorm1 = fabs(ft);
+            const double actred = (fnorm1 < fnorm) ? 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm) : -1.0;
+            const double pred = qtf + r * p;
+            const double prered = (fabs(pred) < fnorm) ? 1.0 - (fabs(pred) / fnorm) * (fabs(pred) / fnorm) : 0.0;
+            const double ratio = (prered > 0.0) ? actred / prered : 0.0;
+            if (ratio < 0.1) { ncsuc = 0; ++ncfail; delta = 0.5 * delta; }
+            else {
+                ncfail = 0; ++ncsuc;
+                if (ratio >= 0.5 || ncsuc > 1) delta = fmax(delta, pnorm / 0.5);
+                if (fabs(ratio - 1.0) <= 0.1) delta = pnorm / 0.5;
+            }
+            if (ratio >= 1e-4) { x = xt; fv = ft; xnorm = fabs(d * x); fnorm = fnorm1; ++iter; }
+            ++nslow1; if (actred >= 1e-3) nslow1 = 0;
+            if (jeval) ++nslow2;
+            if (actred >= 0.1) nslow2 = 0;
+            if (delta <= xtol * xnorm || fnorm == 0.0) finished = true;                     // info 1
+            else if (nfev >= maxfev) finished = true;                                       // info 2
+            else if (0.1 * fmax(0.1 * delta, pnorm) <= epsmch * xnorm) finished = true;     // info 3
+            else if (nslow2 == 5 || nslow1 == 10) finished = true;                          // info 4 / 5
+            else if (ncfail == 2) start_outer();                                            // re-evaluate the Jacobian
+            else {
+                const double s = q * ft, v = (s - pred) / pnorm, uu = d * ((d * p) / pnorm);   // Broyden rank-1 update
+                if (ratio >= 1e-4) qtf = s;
+                r = r + uu * v; jeval = false;
+                need_dogleg = true;
+            }
         }
-        const double ft = fe;
-        const double fnorm1 = fabs(ft);
-        const double actred = (fnorm1 < fnorm) ? 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm) : -1.0;
-        const double pred = qtf + r * p;
-        const double prered = (fabs(pred) < fnorm) ? 1.0 - (fabs(pred) / fnorm) * (fabs(pred) / fnorm) : 0.0;
-        const double ratio = (prered > 0.0) ? actred / prered : 0.0;
-        if (ratio < 0.1) { ncsuc = 0; ++ncfail; delta = 0.5 * delta; }
-        else {
-            ncfail = 0; ++ncsuc;
-            if (ratio >= 0.5 || ncsuc > 1) delta = fmax(delta, pnorm / 0.5);
-            if (fabs(ratio - 1.0) <= 0.1) delta = pnorm / 0.5;
-        }
-        if (ratio >= 1e-4) { x = xt; fv = ft; xnorm = fabs(d * x); fnorm = fnorm1; ++iter; }
-        ++nslow1; if (actred >= 1e-3) nslow1 = 0;
-        if (jeval) ++nslow2;
-        if (actred >= 0.1) nslow2 = 0;
-        if (delta <= xtol * xnorm || fnorm == 0.0) return true;               // info 1
-        if (nfev >= maxfev) return true;                                      // info 2
-        if (0.1 * fmax(0.1 * delta, pnorm) <= epsmch * xnorm) return true;    // info 3
-        if (nslow2 == 5 || nslow1 == 10) return true;                         // info 4 / 5
-        if (ncfail == 2) { start_outer(); return false; }                     // re-evaluate the Jacobian
-        const double s = q * ft, v = (s - pred) / pnorm, uu = d * ((d * p) / pnorm);   // Broyden rank-1 update
-        if (ratio >= 1e-4) qtf = s;
-        r = r + uu * v; jeval = false;
-        dogleg();
-        return false;
+        if (need_dogleg) dogleg();
+        return finished;
     }
 };
 

@@ -1,0 +1,213 @@
+"""ppo_continuous -- drop-in for the reference's ppo_continuous.py with the hot parts on CUDA kernels.
+
+Same classes, parameter names and checkpoint files as the reference, so model_file/one_layer/agent_pursuer_* load
+unchanged (ppo_continuous.py:61-134, 252-258):
+  choose_action -> fused Gaussian-actor kernel (forward + Philox sampling + log-prob), batch 1 or [N, 18]
+  update        -> critic values, sat_gae_flat reverse scan, advantage normalisation kernel; the K-epoch clipped-PPO
+                   minibatch loop stays PyTorch on the GPU with a gradient all-reduce when
+                   torch.distributed is initialised (one flat bucket per network, NCCL over NVLink).
+Only the Gaussian policy is on the CUDA path (policy_dist == "Beta" is out of the north star's scope).
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.distributions import Normal
+
+try:
+    from ._boot import engine as _eng
+except ImportError:
+    from _boot import engine as _eng
+
+
+def orthogonal_init(layer, gain=1.0):
+    nn.init.orthogonal_(layer.weight, gain=gain)
+    nn.init.constant_(layer.bias, 0)
+
+
+class Actor_Gaussian(nn.Module):
+    def __init__(self, args, agent_idx):
+        super().__init__()
+        self.agent_name = 'agent_%s' % agent_idx
+        self.chkpt_file = os.path.join(args.chkpt_dir, self.agent_name + '_actor_Gaussian')
+        self.max_action = args.max_action
+        self.fc1 = nn.Linear(args.state_dim, args.hidden_width)
+        self.fc2 = nn.Linear(args.hidden_width, args.hidden_width)
+        self.mean_layer = nn.Linear(args.hidden_width, args.action_dim)
+        self.log_std = nn.Parameter(torch.zeros(1, args.action_dim))
+        self.activate_func = [nn.ReLU(), nn.Tanh()][args.use_tanh]
+        if args.use_orthogonal_init:
+            orthogonal_init(self.fc1)
+            orthogonal_init(self.fc2)
+            orthogonal_init(self.mean_layer, gain=0.01)
+
+    def forward(self, s):
+        s = self.activate_func(self.fc1(s))
+        s = self.activate_func(self.fc2(s))
+        return self.max_action * torch.tanh(self.mean_layer(s))
+
+    def get_dist(self, s):
+        mean = self.forward(s)
+        return Normal(mean, torch.exp(self.log_std.expand_as(mean)))
+
+    def save_checkpoint(self):
+        torch.save(self.state_dict(), self.chkpt_file)
+
+    def load_checkpoint(self):
+        self.load_state_dict(torch.load(self.chkpt_file, map_location="cpu"))
+
+
+class Critic(nn.Module):
+    def __init__(self, args, agent_idx):
+        super().__init__()
+        self.agent_name = 'agent_%s' % agent_idx
+        self.chkpt_file = os.path.join(args.chkpt_dir, self.agent_name + '_critic')
+        self.fc1 = nn.Linear(args.state_dim, args.hidden_width)
+        self.fc2 = nn.Linear(args.hidden_width, args.hidden_width)
+        self.fc3 = nn.Linear(args.hidden_width, 1)
+        self.activate_func = [nn.ReLU(), nn.Tanh()][args.use_tanh]
+        if args.use_orthogonal_init:
+            orthogonal_init(self.fc1)
+            orthogonal_init(self.fc2)
+            orthogonal_init(self.fc3)
+
+    def forward(self, s):
+        s = self.activate_func(self.fc1(s))
+        s = self.activate_func(self.fc2(s))
+        return self.fc3(s)
+
+    def save_checkpoint(self):
+        torch.save(self.state_dict(), self.chkpt_file)
+
+    def load_checkpoint(self):
+        self.load_state_dict(torch.load(self.chkpt_file, map_location="cpu"))
+
+
+def allreduce_grads_(module, group=None):
+    """Average gradients across ranks with ONE flat all-reduce per network (286 KB actor / 284 KB critic)."""
+    dist = torch.distributed
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+class PPO_continuous:
+    def __init__(self, args, agent_idx, device="cuda", seed=0):
+        if getattr(args, "policy_dist", "Gaussian") != "Gaussian":
+            raise NotImplementedError("only the Gaussian policy is on the CUDA path")
+        self.device = torch.device(device)
+        self.policy_dist = args.policy_dist
+        self.max_action, self.batch_size, self.mini_batch_size = args.max_action, args.batch_size, args.mini_batch_size
+        self.max_train_steps, self.lr_a, self.lr_c = args.max_train_steps, args.lr_a, args.lr_c
+        self.gamma, self.lamda, self.epsilon, self.K_epochs = args.gamma, args.lamda, args.epsilon, args.K_epochs
+        self.entropy_coef, self.set_adam_eps = args.entropy_coef, args.set_adam_eps
+        self.use_grad_clip, self.use_lr_decay, self.use_adv_norm = args.use_grad_clip, args.use_lr_decay, args.use_adv_norm
+        self.actor = Actor_Gaussian(args, agent_idx).to(self.device)
+        self.critic = Critic(args, agent_idx).to(self.device)
+        eps = dict(eps=1e-5) if self.set_adam_eps else {}
+        self.optimizer_actor = torch.optim.Adam(self.actor.parameters(), lr=self.lr_a, **eps)
+        self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=self.lr_c, **eps)
+        self._use_tanh = bool(args.use_tanh)
+        self.actor_kernel = _eng.GaussianActorKernel(max_action=self.max_action, use_tanh=self._use_tanh, device=self.device)
+        self.critic_kernel = _eng.GaussianActorKernel(use_tanh=self._use_tanh, device=self.device, critic=True)
+        self.seed, self._step = int(seed) + (hash(str(agent_idx)) & 0xffff), 0
+        self._dirty = True
+
+    # ---- kernel-side weight image follows the torch parameters
+    def sync_kernels(self):
+        self.actor_kernel.load_state_dict(self.actor.state_dict())
+        self.critic_kernel.load_state_dict(self.critic.state_dict())
+        self._dirty = False
+
+    def _obs(self, s):
+        a = np.asarray(s, dtype=np.float32)
+        return torch.as_tensor(np.ascontiguousarray(a.reshape(-1, a.shape[-1])), device=self.device), a.ndim == 1
+
+    def evaluate(self, s):
+        x, one = self._obs(s)
+        with torch.no_grad():
+            a = self.actor(x).cpu().numpy()
+        return a.flatten() if one else a
+
+    def choose_action(self, s):
+        """(a, a_logprob) as float32 numpy, flattened for a single observation (ppo_continuous.py:176-189)."""
+        if self._dirty:
+            self.sync_kernels()
+        x, one = self._obs(s)
+        a, lp = self.actor_kernel.sample(obs=x, seed=self.seed, step=self._step)
+        self._step += 1
+        out = torch.cat([a, lp], dim=1).cpu().numpy()
+        a, lp = out[:, :a.shape[1]], out[:, a.shape[1]:]
+        return (a.flatten(), lp.flatten()) if one else (a, lp)
+
+    # ---- PPO update
+    def update(self, replay_buffer, total_steps):
+        s, a, a_logprob, r, s_, dw, done = (t.to(self.device) for t in replay_buffer.numpy_to_tensor())
+        with torch.no_grad():                                              # :198-210
+            vs, vs_ = self.critic(s), self.critic(s_)
+            adv, v_target = _eng.gae_flat(r, vs, vs_, dw, done, self.gamma, self.lamda)
+            adv, v_target = adv.view(-1, 1), v_target.view(-1, 1)
+            if self.use_adv_norm:
+                _eng.adv_normalize_(adv, group=False)
+        self.optimize(s, a, a_logprob, adv, v_target)
+        if self.use_lr_decay:
+            self.lr_decay(total_steps)
+
+    def optimize(self, s, a, a_logprob, adv, v_target, mini_batch_size=None, group=None):
+        """K epochs of clipped-PPO minibatch steps (ppo_continuous.py:213-239) on device tensors."""
+        B = s.shape[0]
+        mb = mini_batch_size or self.mini_batch_size
+        for _ in range(self.K_epochs):
+            perm = torch.randperm(B, device=s.device)
+            for lo in range(0, B, mb):
+                index = perm[lo:lo + mb]
+                dist_now = self.actor.get_dist(s[index])
+                dist_entropy = dist_now.entropy().sum(1, keepdim=True)
+                a_logprob_now = dist_now.log_prob(a[index])
+                ratios = torch.exp(a_logprob_now.sum(1, keepdim=True) - a_logprob[index].sum(1, keepdim=True))
+                surr1 = ratios * adv[index]
+                surr2 = torch.clamp(ratios, 1 - self.epsilon, 1 + self.epsilon) * adv[index]
+                actor_loss = -torch.min(surr1, surr2) - self.entropy_coef * dist_entropy
+                self.optimizer_actor.zero_grad()
+                actor_loss.mean().backward()
+                allreduce_grads_(self.actor, group)
+                if self.use_grad_clip:
+                    torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.5)
+                self.optimizer_actor.step()
+                v_s = self.critic(s[index])
+                critic_loss = F.mse_loss(v_target[index], v_s)
+                self.optimizer_critic.zero_grad()
+                critic_loss.backward()
+                allreduce_grads_(self.critic, group)
+                if self.use_grad_clip:
+                    torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 0.5)
+                self.optimizer_critic.step()
+        self._dirty = True
+
+    def lr_decay(self, total_steps):
+        lr_a_now = self.lr_a * (1 - total_steps / self.max_train_steps)
+        lr_c_now = self.lr_c * (1 - total_steps / self.max_train_steps)
+        for p in self.optimizer_actor.param_groups:
+            p['lr'] = lr_a_now
+        for p in self.optimizer_critic.param_groups:
+            p['lr'] = lr_c_now
+
+    def save_checkpoint(self):
+        self.actor.save_checkpoint()
+        self.critic.save_checkpoint()
+
+    def load_checkpoint(self):
+        self.actor.load_checkpoint()
+        self.critic.load_checkpoint()
+        self.actor.to(self.device)
+        self.critic.to(self.device)
+        self._dirty = True

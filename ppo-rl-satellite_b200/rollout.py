@@ -1,0 +1,102 @@
+"""Batched on-device rollout + PPO update (BASELINE config 5): N envs x T steps per GPU, everything resident in HBM.
+
+Per step: pursuer actor kernel (observation rebuilt + normalised from the fp64 state, Philox sample) -> evader actor
+kernel -> fused env step (statistics updated in-kernel). After T steps: critic values, time-major GAE kernel,
+advantage normalisation with all-reduced moments, then the K-epoch minibatch update (PyTorch + NCCL gradient
+all-reduce). Envs shard across ranks with no traffic during the rollout."""
+from __future__ import annotations
+
+import torch
+
+from . import engine as eng
+
+
+class RolloutBuffer:
+    """time-major device storage; s_ is implicit (obs[t+1]) because done == dw in this env."""
+
+    def __init__(self, T: int, n: int, device="cuda"):
+        self.T, self.n = T, n
+        d = torch.device(device)
+        self.obs = torch.empty((T + 1, n, 18), dtype=torch.float32, device=d)
+        self.act = torch.empty((T, n, 3), dtype=torch.float32, device=d)
+        self.logp = torch.empty((T, n, 3), dtype=torch.float32, device=d)
+        self.opp_act = torch.empty((T, n, 3), dtype=torch.float32, device=d)
+        self.opp_logp = torch.empty((T, n, 3), dtype=torch.float32, device=d)
+        self.rew64 = torch.empty((T, n), dtype=torch.float64, device=d)
+        self.done = torch.empty((T, n), dtype=torch.uint8, device=d)
+        self.ret_std = torch.ones(T, dtype=torch.float64, device=d)
+        self.values = torch.empty((T + 1, n), dtype=torch.float32, device=d)
+        self.adv = torch.empty((T, n), dtype=torch.float32, device=d)
+        self.v_target = torch.empty((T, n), dtype=torch.float32, device=d)
+
+    @property
+    def bytes_per_sample(self):
+        return 18 * 4 + 4 * 3 * 4 + 8 + 1 + 3 * 4
+
+
+class VectorTrainer:
+    """Drives `agent` (learner: pursuer for flag 0, evader for flag 1) against `opponent` on an EnvBatch."""
+
+    def __init__(self, env: eng.EnvBatch, agent, opponent, T: int, use_state_norm=True, use_reward_scaling=True,
+                 rank: int = 0, seed: int = 0):
+        self.env, self.agent, self.opponent, self.T = env, agent, opponent, T
+        self.buf = RolloutBuffer(T, env.n, env.device)
+        self.obs_stats = eng.RunningStats(18, env.device) if use_state_norm else None
+        self.ret_stats = eng.RunningStats(1, env.device) if use_reward_scaling else None
+        self.row_offset = rank * env.n
+        self.seed = seed
+        self.t_global = 0
+        if self.obs_stats is not None:
+            self.obs_stats.update_normalize(env.observe())          # statistics of the initial observations
+        self.learner_is_pursuer = env.params.flag == 0
+
+    def collect(self):
+        env, buf = self.env, self.buf
+        if self.agent._dirty:
+            self.agent.sync_kernels()
+        if self.opponent._dirty:
+            self.opponent.sync_kernels()
+        for t in range(self.T):
+            g = self.t_global
+            self.agent.actor_kernel.sample(env=env, obs_stats=self.obs_stats, seed=self.seed, step=2 * g,
+                                           row_offset=self.row_offset, act=buf.act[t], logp=buf.logp[t], obs_out=buf.obs[t])
+            self.opponent.actor_kernel.sample(env=env, obs_stats=self.obs_stats, seed=self.seed, step=2 * g + 1,
+                                              row_offset=self.row_offset, act=buf.opp_act[t], logp=buf.opp_logp[t])
+            pa, ea = (buf.act[t], buf.opp_act[t]) if self.learner_is_pursuer else (buf.opp_act[t], buf.act[t])
+            env.step(pa, ea, reward=buf.rew64[t], done=buf.done[t], obs_stats=self.obs_stats, ret_stats=self.ret_stats,
+                     ret_std_out=buf.ret_std[t:t + 1] if self.ret_stats is not None else None)
+            self.t_global += 1
+        # observation after the last step (bootstrap value), normalised with the current statistics
+        x = env.observe()
+        if self.obs_stats is not None:
+            x = (x - self.obs_stats.mean) / (self.obs_stats.std + 1e-8)
+        buf.obs[self.T] = x.float()
+
+    def compute_advantages(self, group=None):
+        buf, ag = self.buf, self.agent
+        T, n = self.T, self.env.n
+        ag.critic_kernel.value(buf.obs.view(-1, 18), out=buf.values.view(-1))
+        r32 = buf.rew64.float()
+        r_scale = (1.0 / (buf.ret_std + 1e-8)).float() if self.ret_stats is not None else None
+        eng.gae_time_major(r32, buf.values, buf.done, ag.gamma, ag.lamda, r_scale=r_scale, adv=buf.adv, v_target=buf.v_target)
+        if ag.use_adv_norm:
+            eng.adv_normalize_(buf.adv, group=group)
+        return buf.adv, buf.v_target
+
+    def update(self, mini_batch_size: int, total_steps: int = 0, group=None):
+        buf, ag = self.buf, self.agent
+        adv, v_target = self.compute_advantages(group)
+        B = self.T * self.env.n
+        ag.optimize(buf.obs[:self.T].reshape(B, 18), buf.act.reshape(B, 3), buf.logp.reshape(B, 3), adv.reshape(B, 1),
+                    v_target.reshape(B, 1), mini_batch_size=mini_batch_size, group=group)
+        if ag.use_lr_decay:
+            ag.lr_decay(total_steps)
+        ag.sync_kernels()
+
+
+def shard_bounds(n_total: int, world: int, rank: int):
+    """contiguous env shard of rank: [lo, hi)"""
+    per = n_total // world
+    rem = n_total % world
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)

@@ -1,0 +1,204 @@
+"""GPU tests of the reference-named drop-in modules (the surface CPPO_main.py touches) and of the batched trainer."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "ppo-rl-satellite_b200", "dropin")
+
+
+class Args:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def ppo_args(tmpdir, **over):
+    a = dict(policy_dist="Gaussian", max_action=1.6, batch_size=64, mini_batch_size=16, max_train_steps=5000,
+             lr_a=2e-4, lr_c=2e-4, gamma=0.99, lamda=0.95, epsilon=0.1, K_epochs=3, entropy_coef=0.01, set_adam_eps=True,
+             use_grad_clip=True, use_lr_decay=True, use_adv_norm=True, state_dim=18, action_dim=3, hidden_width=256,
+             use_tanh=True, use_orthogonal_init=True, chkpt_dir=str(tmpdir), max_episode_steps=64)
+    a.update(over)
+    return Args(**a)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    """import the drop-ins the way CPPO_main.py would: as top-level modules named like the reference's."""
+    sys.path.insert(0, DROPIN)
+    for k in ("environment", "satellite_function", "ppo_continuous", "replaybuffer", "normalization", "orbit_rk4"):
+        sys.modules.pop(k, None)
+    import environment, satellite_function, ppo_continuous, replaybuffer, normalization, orbit_rk4
+    yield Args(environment=environment, sf=satellite_function, ppo=ppo_continuous, rb=replaybuffer,
+               norm=normalization, rk4=orbit_rk4)
+    sys.path.remove(DROPIN)
+
+
+def test_satellites_reset_step_contract_matches_reference_rollout(golden, mods):
+    """config 1 plumbing: the (obs, reward, done) stream of the reference env under its recorded action stream."""
+    g = golden("env_golden.npz")
+    env = mods.environment.satellites(Pursuer_position=np.array([2000000, 2000000, 1000000]),
+                                      Pursuer_vector=np.array([1710, 1140, 1300]),
+                                      Escaper_position=np.array([1850000, 2000000, 1000000]),
+                                      Escaper_vector=np.array([1710, 1140, 1300]), d_capture=50000,
+                                      args=Args(max_episode_steps=64))
+    env.d_capture = 20000                                     # CPPO_main.py:98
+    assert env.observation_space.shape[0] == 18 and env.action_space.shape[0] == 3 and float(env.action_space[0][1]) == 1.6
+    s = env.reset(0)
+    assert s.dtype == np.int64 and np.array_equal(s, g["cfg1_reset_obs"].astype(np.int64))
+    cnt = 0
+    for t in range(200):
+        cnt += 1
+        s_, r, d = env.step(g["cfg1_pa"][t], g["cfg1_ea"][t], cnt)
+        assert isinstance(d, bool) and s_.shape == (18,)
+        assert np.array_equal(s_, g["cfg1_obs"][t]) and r == g["cfg1_reward"][t] and d == bool(g["cfg1_done"][t])
+        assert env.dangerous_zone == g["cfg1_dz"][t] and env.fuel_c == g["cfg1_fuel_c"][t] and env.dis == g["cfg1_dis"][t]
+        if d:
+            env.reset(0)
+            cnt = 0
+    with pytest.raises(NotImplementedError):
+        env.reset(2)
+
+
+def test_driver_loop_like_cppo_main(golden, mods, tmp_path):
+    """the loop of train_pursuer_network (CPPO_main.py:111-153) on the drop-in modules: 3 episodes, updates included."""
+    args = ppo_args(tmp_path)
+    env = mods.environment.satellites(d_capture=50000, args=args)
+    env.d_capture = 15000
+    args.state_dim = env.observation_space.shape[0]
+    args.action_dim = env.action_space.shape[0]
+    args.max_action = float(env.action_space[0][1])
+    buf = mods.rb.ReplayBuffer(args)
+    pursuer, evader = mods.ppo.PPO_continuous(args, 'pursuer'), mods.ppo.PPO_continuous(args, 'evader')
+    before = [p.detach().clone() for p in pursuer.actor.parameters()]
+    n_updates = 0
+    for episode in range(3):
+        s = env.reset(0)
+        count = 0
+        while True:
+            count += 1
+            a, lp = pursuer.choose_action(s)
+            ea, _ = evader.choose_action(s)
+            assert a.shape == (3,) and lp.shape == (3,) and a.dtype == np.float32 and np.all(np.abs(a) <= 1.6 + 1e-6)
+            s_, r, done = env.step(a, ea, count)
+            dw = bool(done or count >= args.max_episode_steps)
+            buf.store(s, a, lp, r, s_, dw, done)
+            s = s_
+            if buf.count == args.batch_size:
+                pursuer.update(buf, episode)
+                buf.count = 0
+                n_updates += 1
+            if done:
+                break
+    assert n_updates >= 2
+    assert any(not torch.equal(b, p.detach()) for b, p in zip(before, pursuer.actor.parameters()))
+    assert all(torch.isfinite(p).all() for p in pursuer.actor.parameters())
+    # kernel-side weights follow the torch parameters after an update
+    x = torch.randn(32, 18, device="cuda")
+    mean = torch.empty(32, 3, device="cuda")
+    pursuer.sync_kernels()
+    pursuer.actor_kernel.sample(obs=x, eps_in=torch.zeros(32, 3, device="cuda"), mean_out=mean)
+    with torch.no_grad():
+        torch.testing.assert_close(mean, pursuer.actor(x), rtol=0, atol=3e-5)
+    pursuer.save_checkpoint()
+    again = mods.ppo.PPO_continuous(args, 'pursuer')
+    again.load_checkpoint()
+    assert all(torch.equal(a, b) for a, b in zip(again.actor.state_dict().values(), pursuer.actor.state_dict().values()))
+    assert os.path.exists(os.path.join(str(tmp_path), "agent_pursuer_actor_Gaussian"))
+
+
+def test_reference_checkpoint_loads_and_acts(golden, mods, tmp_path):
+    """the shipped one_layer/agent_pursuer_* pair (stored in the fixture as its state_dict) loads by name."""
+    g = golden("ppo_golden.npz")
+    args = ppo_args(tmp_path)
+    torch.save({k[len("actor."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("actor.")},
+               os.path.join(str(tmp_path), "agent_pursuer_actor_Gaussian"))
+    torch.save({k[len("critic."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("critic.")},
+               os.path.join(str(tmp_path), "agent_pursuer_critic"))
+    agent = mods.ppo.PPO_continuous(args, 'pursuer')
+    agent.load_checkpoint()
+    np.testing.assert_allclose(agent.evaluate(g["obs"][400]), g["mean"][400], rtol=0, atol=2e-5)
+    a, lp = agent.choose_action(g["obs"][384:])
+    assert a.shape == (384, 3) and np.all(np.isfinite(lp))
+
+
+def test_satellite_function_helpers(golden, mods):
+    ge, gv = golden("elements_golden.npz"), golden("env_golden.npz")
+    T = mods.sf.Time_window_of_danger_zone
+    for k in range(0, 841, 60):
+        el = T.calculate_orbital_elements(3.986e14, ge["R"][k], ge["V"][k])
+        np.testing.assert_allclose(el, ge["elements_live"][k], rtol=1e-12, atol=1e-12)
+        R, V = T.calculate_state_information(list(ge["elements_live"][k]), miu=3.986e14)
+        np.testing.assert_allclose(np.concatenate([R, V]), ge["state_roundtrip"][k], rtol=1e-12, atol=1e-8)
+    els, kind = mods.sf.orbital_elements_batch(3.986e14, np.concatenate([ge["R"], ge["V"]], axis=1))
+    assert np.all(kind == 6)
+    csv = ge["csv_a_e_i_f_fuel"]                               # the reference's own stored answers
+    assert np.max(np.abs(els[:, 0] - csv[:, 0]) / csv[:, 0]) < 1e-14 and np.max(np.abs(els[:, 1] - csv[:, 1])) < 1e-13
+    assert np.max(np.abs(els[:, 2] - csv[:, 2])) < 1e-11
+    # CW STM applied to both craft: bit-identical to numpy's dgemv on the reference matrix
+    rng = np.random.default_rng(0)
+    Rc, Vc, Rt, Vt = rng.normal(0, 1e5, 3), rng.normal(0, 3, 3), rng.normal(0, 1e5, 3), rng.normal(0, 3, 3)
+    sc, st = mods.sf.Clohessy_Wiltshire(R0_c=Rc, V0_c=Vc, R0_t=Rt, V0_t=Vt).State_transition_matrix(100)
+    M = gv["stm100_columns"]
+    assert np.array_equal(sc, np.dot(M, np.concatenate([Rc, Vc]))) and np.array_equal(st, np.dot(M, np.concatenate([Rt, Vt])))
+    gd = golden("danger_golden.npz")
+    for k in (0, 5, 900, 2000):
+        S = gd["dz_states"][k]
+        obj = T(R0_c=S[0:3].copy(), V0_c=S[3:6].copy(), R0_t=S[6:9].copy(), V0_t=S[9:12].copy(), Delta_V_c=gd["dz_fuel"][k], time_step=1)
+        assert obj.calculate_number_of_hanger_area() == gd["dz_count"][k]
+
+
+def test_orbit_rk4_script_functions(golden, mods):
+    g = golden("rk4_golden.npz")
+    for p, f in zip(g["stateeq_in"], g["stateeq_out"]):
+        np.testing.assert_allclose(mods.rk4.StateEq(0, p), f, rtol=1e-13, atol=0)
+    rv = g["script_ic"].copy()
+    for i in range(5):
+        rv = mods.rk4.RungeKutta(i, rv, 1)
+    ref = g["script_ic"].copy()
+    from oracle import oracle as O
+    ref = O.rk4_propagate(ref.reshape(6, 1), 1.0, 5)[:, 0]
+    np.testing.assert_allclose(rv, ref, rtol=1e-13)
+    out = mods.rk4.RungeKutta(0, g["x0"], 1.0, steps=1000)
+    dr = np.linalg.norm(out[:3] - g["x1000_j2on"][:3], axis=0) / np.linalg.norm(g["x1000_j2on"][:3], axis=0)
+    assert dr.max() < 1e-9
+
+
+def test_normalization_module(golden, mods):
+    g = golden("norm_golden.npz")
+    nz = mods.norm.Normalization(shape=18)
+    for k in range(60):
+        assert np.array_equal(nz(g["x"][k].copy()), g["x_normed"][k])
+    rs = mods.norm.RewardScaling(shape=1, gamma=0.99)
+    for k in range(60):
+        assert float(np.ravel(rs(g["reward"][k]))[0]) == g["reward_scaled"][k]
+        if g["done"][k]:
+            rs.reset()
+    assert nz.running_ms.n == 60 and nz.running_ms.mean.shape == (18,)
+
+
+def test_vector_trainer_collect_and_update(oracle, mods, tmp_path):
+    from ppo_rl_satellite_b200 import engine as eng, rollout
+    n, T = 512, 8
+    args = ppo_args(tmp_path, K_epochs=2)
+    env = eng.EnvBatch(n, mode="cw", d_capture=20000.0, max_episode_steps=5, auto_reset=True)
+    agent, opp = mods.ppo.PPO_continuous(args, 'pursuer'), mods.ppo.PPO_continuous(args, 'evader')
+    tr = rollout.VectorTrainer(env, agent, opp, T)
+    tr.collect()
+    buf = tr.buf
+    assert torch.isfinite(buf.obs).all() and buf.done.sum() > 0 and torch.all(buf.act.abs() <= 1.6 + 1e-6)
+    adv, vt = tr.compute_advantages(group=False)
+    # GAE on the buffer's own data vs the oracle (column-wise reference block), before normalisation is undone
+    r32 = (buf.rew64.float() * (1.0 / (buf.ret_std + 1e-8)).float()[:, None]).cpu().numpy()
+    o_adv, o_vt = oracle.gae_time_major(r32, buf.values.cpu().numpy(), buf.done.cpu().numpy())
+    assert np.array_equal(vt.cpu().numpy(), o_vt)
+    a = o_adv.astype(np.float64)
+    np.testing.assert_allclose(adv.cpu().numpy(), (a - a.mean()) / (a.std(ddof=1) + 1e-5), rtol=2e-5, atol=2e-5)
+    before = [p.detach().clone() for p in agent.critic.parameters()]
+    tr.update(mini_batch_size=1024)
+    assert any(not torch.equal(b, p.detach()) for b, p in zip(before, agent.critic.parameters()))
+    assert tr.obs_stats.n == n * (T + 1)
