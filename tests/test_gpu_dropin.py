@@ -126,7 +126,7 @@ def test_reference_checkpoint_loads_and_acts(golden, mods, tmp_path):
     assert a.shape == (384, 3) and np.all(np.isfinite(lp))
 
 
-def test_satellite_function_helpers(golden, mods):
+def test_satellite_function_helpers(golden, oracle, mods):
     ge, gv = golden("elements_golden.npz"), golden("env_golden.npz")
     T = mods.sf.Time_window_of_danger_zone
     for k in range(0, 841, 60):
@@ -139,12 +139,18 @@ def test_satellite_function_helpers(golden, mods):
     csv = ge["csv_a_e_i_f_fuel"]                               # the reference's own stored answers
     assert np.max(np.abs(els[:, 0] - csv[:, 0]) / csv[:, 0]) < 1e-14 and np.max(np.abs(els[:, 1] - csv[:, 1])) < 1e-13
     assert np.max(np.abs(els[:, 2] - csv[:, 2])) < 1e-11
-    # CW STM applied to both craft: bit-identical to numpy's dgemv on the reference matrix
+    # CW STM applied to both craft: bit-identical to the dgemv summation order pinned in the build container
+    # (oracle.cw_apply). NOT compared with np.dot on this host: OpenBLAS dispatches a different dgemv kernel per CPU
+    # model, and on the GPU box's host np.dot itself differs from the build container's in the last bit for some
+    # inputs (observed; DESIGN.md "numpy arithmetic the env relies on").
     rng = np.random.default_rng(0)
-    Rc, Vc, Rt, Vt = rng.normal(0, 1e5, 3), rng.normal(0, 3, 3), rng.normal(0, 1e5, 3), rng.normal(0, 3, 3)
-    sc, st = mods.sf.Clohessy_Wiltshire(R0_c=Rc, V0_c=Vc, R0_t=Rt, V0_t=Vt).State_transition_matrix(100)
     M = gv["stm100_columns"]
-    assert np.array_equal(sc, np.dot(M, np.concatenate([Rc, Vc]))) and np.array_equal(st, np.dot(M, np.concatenate([Rt, Vt])))
+    for _ in range(20):
+        Rc, Vc, Rt, Vt = rng.normal(0, 1e5, 3), rng.normal(0, 3, 3), rng.normal(0, 1e5, 3), rng.normal(0, 3, 3)
+        sc, st = mods.sf.Clohessy_Wiltshire(R0_c=Rc, V0_c=Vc, R0_t=Rt, V0_t=Vt).State_transition_matrix(100)
+        assert np.array_equal(sc, oracle.cw_apply(M, np.concatenate([Rc, Vc])))
+        assert np.array_equal(st, oracle.cw_apply(M, np.concatenate([Rt, Vt])))
+        np.testing.assert_allclose(st, np.dot(M, np.concatenate([Rt, Vt])), rtol=1e-15, atol=0)
     gd = golden("danger_golden.npz")
     for k in (0, 5, 900, 2000):
         S = gd["dz_states"][k]
