@@ -143,7 +143,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": f"{n_envs} envs x {args.steps} steps (S={args.substeps} RK4+J2 substeps, env step only, actions given)"},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args):
@@ -346,10 +346,26 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was moved to stderr"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # libraries that print to fd 1 (NCCL version banner) now land on stderr
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
