@@ -30,6 +30,10 @@ using namespace sat;
 constexpr int kBlock = 128;             // finish / fused kernels: threads per CTA (2 lanes per env)
 constexpr int kEnvsPerBlock = kBlock / 2;
 constexpr int kFrontBlock = 64;         // rk4 front (impulse + propagation) kernel
+// kernel B is latency bound (long dependent FP64 chains: divisions, sqrt, acos, sincos): measured on B200 at 65 536
+// envs, total env-step time vs min-blocks-per-SM {1: 250, 4: 200, 7: 185, 8: 187, 10: 201, 12: 231} us. 7 CTAs x 128
+// threads at 72 registers (some spills to L1) beats 186 registers at 2 CTAs.
+constexpr int kFinishMinBlocks = 7;
 constexpr int kObs = 18;
 constexpr int kStatDims = 19;           // 18 observation dims + discounted return
 constexpr int kWsHeader = 256;          // workspace: [ticket counter | pad] [dis_prev: n doubles] [partials]
@@ -199,17 +203,21 @@ SAT_DEV void queue_run(SolveQueue& q) {
 // partials, auto-reset. environment.py:130-179 / :212-255, :317-343, :346-396.
 // FUSED = true: front half in the same kernel (cw mode, where propagation is one 6x6 product).
 // ---------------------------------------------------------------------------------------------
-template <bool FUSED, typename ActT>
-__global__ void __launch_bounds__(kBlock)
+template <bool FUSED, typename ActT, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* __restrict__ ea,
                 const int32_t* __restrict__ count_override, float* __restrict__ obs_f32,
                 double* __restrict__ obs_f64, double* __restrict__ term_obs_f64,
                 double* __restrict__ reward_out, uint8_t* __restrict__ done_out,
                 const double* __restrict__ dis_prev_in, double* __restrict__ partials,
                 unsigned int* __restrict__ ticket, const __grid_constant__ SatEnvParams p) {
-    __shared__ double tile[kEnvsPerBlock][kStatDims];        // next observation (+ return) of the CTA's envs
-    __shared__ double tile_term[kEnvsPerBlock][kObs];        // pre-reset observation
-    __shared__ SolveQueue queue;
+    // the solve queue and the observation tiles are live at different times: one shared-memory block, two views
+    struct Tiles { double tile[kEnvsPerBlock][kStatDims]; double tile_term[kEnvsPerBlock][kObs]; };
+    union SharedBlock { SolveQueue queue; Tiles tiles; __device__ SharedBlock() {} };
+    __shared__ SharedBlock shm;
+    SolveQueue& queue = shm.queue;
+    double (&tile)[kEnvsPerBlock][kStatDims] = shm.tiles.tile;      // next observation (+ return) of the CTA's envs
+    double (&tile_term)[kEnvsPerBlock][kObs] = shm.tiles.tile_term; // pre-reset observation
     queue_init(queue);
 
     const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -267,6 +275,7 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     queue_run(queue);
     if (slot0 >= 0) alpha0 = queue.alpha[slot0];
     if (slot1 >= 0) alpha1 = queue.alpha[slot1];
+    __syncthreads();                                        // queue storage is reused by the observation tiles below
     const int dz_eval = dz_finalize(need_dz, nd, alpha0, alpha1, nullptr);
     int dz_new = dz_stale;                                   // not refreshed on capture / time-out steps (Q3)
     if (need_dz) {
@@ -685,21 +694,21 @@ int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const in
     if (p->mode == SAT_MODE_CW) {
         // one fused kernel: the propagation is a 6x6 product
         if (p->action_dtype == SAT_ACT_F32)
-            env_step_kernel<true, float><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
+            env_step_kernel<true, float, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, nullptr, partials, ticket, *p);
         else
-            env_step_kernel<true, double><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
+            env_step_kernel<true, double, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, nullptr, partials, ticket, *p);
     } else {
         // kernel A (FP64-pipe bound, <= 72 registers, whole batch resident) then kernel B (register-heavy, divergent)
         const int64_t fblocks = (2 * n + kFrontBlock - 1) / kFrontBlock;
         if (p->action_dtype == SAT_ACT_F32) {
             env_front_rk4_kernel<float><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea, dis_prev, *p);
-            env_step_kernel<false, float><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
+            env_step_kernel<false, float, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
         } else {
             env_front_rk4_kernel<double><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea, dis_prev, *p);
-            env_step_kernel<false, double><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
+            env_step_kernel<false, double, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
         }
     }
