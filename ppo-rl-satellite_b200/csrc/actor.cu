@@ -75,26 +75,36 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 __device__ __forceinline__ float activate(float x, int use_tanh) { return use_tanh ? fast_tanh(x) : fmaxf(x, 0.0f); }
 
-// acc[8][16] += A[k][m0..m0+8) * B[k][cols], k in [0, K); A row stride lda, B row stride HID
+// acc[8][16] += A[k][m0..m0+8) * B[k][cols], k in [0, K); A row stride lda, B row stride HID.
+// The 8 x 16 tile is held as 8 x 8 float2 and updated with Blackwell's packed FFMA2 (fma.rn.f32x2): the same
+// IEEE fp32 FMAs, two per issue slot, which leaves issue bandwidth for the LDS/address instructions.
 template <int K>
-__device__ __forceinline__ void tile_fma(float (&acc)[8][16], const float* __restrict__ A, int lda,
+__device__ __forceinline__ void tile_fma(float2 (&acc)[8][8], const float* __restrict__ A, int lda,
                                          const float* __restrict__ B, int ty, int tx) {
-#pragma unroll 4
+#pragma unroll 2
     for (int k = 0; k < K; ++k) {
         const float4 a0 = *reinterpret_cast<const float4*>(A + k * lda + ty * 8);
         const float4 a1 = *reinterpret_cast<const float4*>(A + k * lda + ty * 8 + 4);
         const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        float b[16];
+        float2 b[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float4 bv = *reinterpret_cast<const float4*>(B + k * HID + c * 64 + tx * 4);
-            b[c * 4 + 0] = bv.x; b[c * 4 + 1] = bv.y; b[c * 4 + 2] = bv.z; b[c * 4 + 3] = bv.w;
+            b[c * 2] = make_float2(bv.x, bv.y); b[c * 2 + 1] = make_float2(bv.z, bv.w);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i) {
+            const float2 ai = make_float2(a[i], a[i]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int j = 0; j < 8; ++j) acc[i][j] = __ffma2_rn(ai, b[j], acc[i][j]);
+        }
     }
+}
+
+// element (row i, local column c*4+q) of the packed accumulator tile
+__device__ __forceinline__ float acc_at(const float2 (&acc)[8][8], int i, int c, int q) {
+    const float2 v = acc[i][c * 2 + (q >> 1)];
+    return (q & 1) ? v.y : v.x;
 }
 
 template <bool CRITIC>
@@ -157,11 +167,11 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
     }
 
     // ---------------- layer 1: h1 = act(W1 x + b1) -> h1T
-    float acc[8][16];
+    float2 acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[i][j] = 0.0f;
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
     mbar_wait(&sm.bar_misc, 0);
     tile_fma<IN>(acc, sm.xT, M, &sm.wt[0][0], ty, tx);
 #pragma unroll
@@ -171,10 +181,10 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
             const int j = c * 64 + tx * 4 + q;
             const float bias = __ldg(packed + OFF_B1 + j);
             float4 lo, hi;
-            lo.x = activate(acc[0][c * 4 + q] + bias, use_tanh); lo.y = activate(acc[1][c * 4 + q] + bias, use_tanh);
-            lo.z = activate(acc[2][c * 4 + q] + bias, use_tanh); lo.w = activate(acc[3][c * 4 + q] + bias, use_tanh);
-            hi.x = activate(acc[4][c * 4 + q] + bias, use_tanh); hi.y = activate(acc[5][c * 4 + q] + bias, use_tanh);
-            hi.z = activate(acc[6][c * 4 + q] + bias, use_tanh); hi.w = activate(acc[7][c * 4 + q] + bias, use_tanh);
+            lo.x = activate(acc_at(acc, 0, c, q) + bias, use_tanh); lo.y = activate(acc_at(acc, 1, c, q) + bias, use_tanh);
+            lo.z = activate(acc_at(acc, 2, c, q) + bias, use_tanh); lo.w = activate(acc_at(acc, 3, c, q) + bias, use_tanh);
+            hi.x = activate(acc_at(acc, 4, c, q) + bias, use_tanh); hi.y = activate(acc_at(acc, 5, c, q) + bias, use_tanh);
+            hi.z = activate(acc_at(acc, 6, c, q) + bias, use_tanh); hi.w = activate(acc_at(acc, 7, c, q) + bias, use_tanh);
             *reinterpret_cast<float4*>(&sm.h1T[j * H1_LD + ty * 8]) = lo;
             *reinterpret_cast<float4*>(&sm.h1T[j * H1_LD + ty * 8 + 4]) = hi;
         }
@@ -192,7 +202,7 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[i][j] = 0.0f;
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
 #pragma unroll 1
     for (int t = 0; t < NT; ++t) {
         const int s = t & 1;
@@ -220,7 +230,7 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
             for (int a = 0; a < 3; ++a) w[a] = (a < heads) ? sm.w3[a * HID + j] : 0.0f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float h = activate(acc[i][c * 4 + q] + bias, use_tanh);
+                const float h = activate(acc_at(acc, i, c, q) + bias, use_tanh);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) if (a < heads) part[i][a] = fmaf(h, w[a], part[i][a]);
             }

@@ -142,6 +142,23 @@ __global__ void state_info_kernel(const double* __restrict__ el, int64_t n, doub
     rv[idx * 6 + 5] = s * (si * (cu + e * co));
 }
 
+// packed FFMA2 (fma.rn.f32x2) chain: the fp32 issue-rate ceiling of sm_100
+__global__ void peak_ffma2_kernel(float* sink, int iters) {
+    float2 a[8];
+    const float2 m = make_float2(1.0000001f, 0.9999999f), c = make_float2(1e-7f, -1e-7f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = make_float2((threadIdx.x + k) * 1e-3f, (threadIdx.x + k) * 2e-3f);
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = __ffma2_rn(a[k], m, c);
+    }
+    float s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y;
+    if (s == -1.2345f) sink[0] = s;
+}
+
 inline int launch_status() {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SAT_OK : (int)e;
@@ -230,8 +247,10 @@ int sat_peak_fp64(double* sink, int blocks, int threads, int iters, double* flop
 
 int sat_peak_fp32(float* sink, int blocks, int threads, int iters, double* flops_out_host, void* stream) {
     if (!sink) return SAT_ERR_NULL;
-    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0) return SAT_ERR_SIZE;
-    peak_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(sink, iters);
+    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters == 0) return SAT_ERR_SIZE;
+    // 16 FMAs per thread per iteration either way: 16 scalar FFMA chains, or (iters < 0) 8 packed FFMA2 chains
+    if (iters < 0) { iters = -iters; peak_ffma2_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(sink, iters); }
+    else peak_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(sink, iters);
     if (flops_out_host) *flops_out_host = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
     return launch_status();
 }

@@ -424,6 +424,8 @@ def measure_vector_peak(dtype="fp64", iters=4096, repeats=5):
     else:
         sink = torch.zeros(1, dtype=torch.float32, device="cuda")
         fn = lib.sat_peak_fp32
+        if dtype == "fp32x2":          # packed FFMA2 chains (negative iters selects them)
+            iters = -iters
     best = 0.0
     for i in range(repeats + 2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
