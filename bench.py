@@ -124,7 +124,7 @@ def run_reference(args, rank, world):
     n_envs = args.cpu_sample_envs or 64 * cores
     # size the sample: one probe step, then as many envs as fit ~3 s per timed step
     rate, _ = cpu_env_steps_per_s(min(n_envs, 8 * cores), 1, args.substeps, cores)
-    n_envs = int(max(cores, min(65536, rate * 3.0)))
+    n_envs = int(max(cores, min(args.envs, rate * 3.0)))
     times = []
     from oracle import oracle as O
     env = O.BatchEnv(n_envs, d_capture=20000.0, max_episode_steps=1000, nthreads=cores)
@@ -269,12 +269,12 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for t in range(args.warmup):
-        step(t)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for t in range(args.warmup):
+        step(t)
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     wall0 = time.perf_counter()
@@ -344,12 +344,11 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": n * world * ke / float(dt.item()), "unit": "env-steps/s",
                "h2d_bytes_per_step": env.h2d_bytes_per_step, "d2h_bytes_per_step": env.d2h_bytes_per_step,
                "api": "EnvBatch.step_host(pa, ea) -> (obs, reward, done): numpy in/out via pinned staging -> sat_env_step_host"}
-    clocks = sampler.stop() if rank == 0 else None
-
     # ---------------- PPO samples/sec (BASELINE config 5 shape, per-GPU share): rollout + GAE + K-epoch update
     ppo = None
     if not args.no_ppo:
         ppo = run_ppo_section(args, rank, world, dev, torch, dist, eng)
+    clocks = sampler.stop() if rank == 0 else None     # sampled from warm-up to the end of every GPU-timed section
 
     if rank != 0:
         return
@@ -358,10 +357,11 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         probe, _ = cpu_env_steps_per_s(8 * cores, 1, S, cores)
-        n_cpu = int(max(cores, min(65536, probe * 5.0)))
-        rate, dt = cpu_env_steps_per_s(n_cpu, 3, S, cores)
+        n_cpu = int(max(cores, min(n, probe * 2.0)))                 # ~2 s of CPU work per step ...
+        k_cpu = int(max(2, min(50, round(12.0 * probe / n_cpu))))     # ... and ~12 s in total
+        rate, dt = cpu_env_steps_per_s(n_cpu, k_cpu, S, cores)
         cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} envs x 3 steps of the same env step (S={S} RK4+J2 substeps both craft + danger zone + reward), "
+               "sample": f"{n_cpu} envs x {k_cpu} steps of the same env step (S={S} RK4+J2 substeps both craft + danger zone + reward), "
                          f"CPU oracle port in C with OpenMP on all {cores} host threads, {dt:.1f} s"}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0

@@ -284,18 +284,30 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     }
 
     // ---------------- reward (:139-147, :161-175, Flag 1 :221-251)
-    double reward;
+    double reward = 0.0, cos_a = 0.0, cos_b = 0.0;
     if (captured) reward = (p.flag == 0) ? 100.0 : -150.0;
     else if (timeout) reward = (p.flag == 0) ? 0.0 : 100.0;
     else {
+        // the four cosines are split over the lane pair (2 each) and swapped: same values, half the latency
+        double ca, cb;
+        if (craft == 0) {
+            ca = cosine3(P, E);                                                               // pv1 :166
+            cb = cosine3(Pv, Ev);                                                             // pv2 :167
+        } else {
+            ca = cosine3(d, Pv);                                                              // pv3 :168
+            cb = 0.0;                                                                         // pv4 :169
+            if (pa_gated[0] != 0.0 && pa_gated[1] != 0.0 && pa_gated[2] != 0.0) cb = -cosine3(d, pa_gated);
+        }
+        cos_a = ca; cos_b = cb;
+    }
+    // (warp-convergent point: the swaps below are executed by every lane)
+    const double oth_a = shfl1(cos_a), oth_b = shfl1(cos_b);
+    if (!captured && !timeout) {
+        const double pv1 = craft == 0 ? cos_a : oth_a, pv2 = craft == 0 ? cos_b : oth_b;
+        const double pv3 = craft == 0 ? oth_a : cos_a, pv4 = craft == 0 ? oth_b : cos_b;
         const double ra = (dis < L.dis_prev) ? 1.0 : -1.0;                                    // :161
         const double rb = (p.d_capture <= dis && dis <= 4.0 * p.d_capture) ? -1.0 : -2.0;     // :162
         const double rc = (dz_new == 0) ? -1.0 : dz_new * 0.5;                                // :164
-        const double pv1 = cosine3(P, E);                                                     // :166
-        const double pv2 = cosine3(Pv, Ev);                                                   // :167
-        const double pv3 = cosine3(d, Pv);                                                    // :168
-        double pv4 = 0.0;                                                                     // :169
-        if (pa_gated[0] != 0.0 && pa_gated[1] != 0.0 && pa_gated[2] != 0.0) pv4 = -cosine3(d, pa_gated);
         double rr = __dadd_rn(__dadd_rn(ra, rb), rc);
         rr = __dadd_rn(rr, pv1);                                                              // :172-175
         rr = __dadd_rn(rr, __dmul_rn(0.6, pv2));

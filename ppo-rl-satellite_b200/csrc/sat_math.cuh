@@ -341,7 +341,7 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     double si_t, ci_t, si_c, ci_c, sdo, cdo, sdo2, cdo2;
     sincos(t.i, &si_t, &ci_t); sincos(c.i, &si_c, &ci_c);
     sincos(c.Omega - t.Omega, &sdo, &cdo);
-    sincos(t.Omega - c.Omega, &sdo2, &cdo2);
+    sdo2 = -sdo; cdo2 = cdo;          // sin/cos of (Omega_t - Omega_c) = -(Omega_c - Omega_t): exact odd/even symmetry
     double temp1 = (si_t * sdo) / (ci_t * si_c - si_t * ci_c * cdo);
     double temp2 = (si_c * sdo2) / (ci_c * si_t - si_c * ci_t * cdo2);
     if (isnan(temp1) || isnan(temp2)) { temp1 = 1.0; temp2 = 1.0; }      // :331-332
