@@ -234,7 +234,6 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     load_and_gate(st, p, pa, ea, e, craft, L, FUSED);
     if (FUSED) propagate_cw(p, L);
     else L.dis_prev = dis_prev_in[e];
-    const double dz_dummy = 0.0; (void)dz_dummy;
     const int dz_stale = I[SAT_ICOL_DZ * ld + e];
     const int count = I[SAT_ICOL_COUNT * ld + e];
     int err = I[SAT_ICOL_ERR * ld + e];

@@ -107,6 +107,14 @@ class RunningStats:
     def std(self):
         return self.buf[1 + 2 * self.dim:1 + 3 * self.dim]
 
+    def state_dict(self):
+        return {"dim": self.dim, "buf": self.buf.detach().cpu().clone()}
+
+    def load_state_dict(self, sd):
+        assert int(sd["dim"]) == self.dim
+        self.buf.copy_(sd["buf"].to(self.buf.device))
+        return self
+
     def update_normalize(self, x, update=True, out_dtype=None):
         """x: CUDA fp64 [n, dim]. Merges the batch (update=True) then returns (x-mean)/(std+1e-8)."""
         torch = L.require_cuda()
@@ -241,6 +249,28 @@ class EnvBatch:
     @property
     def d2h_bytes_per_step(self):
         return self.n * (OBS_DIM * 4 + 8 + 1)
+
+    # -- checkpoint / resume of the full environment state (the reference saves only the networks)
+    def state_dict(self):
+        p = self.params
+        return {"n": self.n, "mode": self.mode, "state": self.state.detach().cpu().clone(),
+                "istate": self.istate.detach().cpu().clone(),
+                "params": {k: (list(getattr(p, k)) if hasattr(getattr(p, k), "__len__") else getattr(p, k))
+                           for k, _t in p._fields_}}
+
+    def load_state_dict(self, sd):
+        if int(sd["n"]) != self.n or sd["mode"] != self.mode:
+            raise L.SatError("checkpoint is for a different batch size / propagation mode")
+        self.state.copy_(sd["state"].to(self.device))
+        self.istate.copy_(sd["istate"].to(self.device))
+        for k, v in sd["params"].items():
+            if isinstance(v, list):
+                arr = getattr(self.params, k)
+                for i, x in enumerate(v):
+                    arr[i] = x
+            else:
+                setattr(self.params, k, v)
+        return self
 
     # -- convenient views (fp64, exact)
     def positions(self):

@@ -94,6 +94,31 @@ class VectorTrainer:
         ag.sync_kernels()
 
 
+    # ---- full-run checkpoint: env SoA state, running normalisers, Philox counter, networks + optimisers
+    def state_dict(self):
+        ag = self.agent
+        return {"env": self.env.state_dict(), "t_global": self.t_global, "seed": self.seed,
+                "obs_stats": self.obs_stats.state_dict() if self.obs_stats is not None else None,
+                "ret_stats": self.ret_stats.state_dict() if self.ret_stats is not None else None,
+                "actor": ag.actor.state_dict(), "critic": ag.critic.state_dict(),
+                "opt_actor": ag.optimizer_actor.state_dict(), "opt_critic": ag.optimizer_critic.state_dict(),
+                "opponent_actor": self.opponent.actor.state_dict()}
+
+    def load_state_dict(self, sd):
+        ag = self.agent
+        self.env.load_state_dict(sd["env"])
+        self.t_global, self.seed = int(sd["t_global"]), int(sd["seed"])
+        if self.obs_stats is not None and sd["obs_stats"] is not None:
+            self.obs_stats.load_state_dict(sd["obs_stats"])
+        if self.ret_stats is not None and sd["ret_stats"] is not None:
+            self.ret_stats.load_state_dict(sd["ret_stats"])
+        ag.actor.load_state_dict(sd["actor"]); ag.critic.load_state_dict(sd["critic"])
+        ag.optimizer_actor.load_state_dict(sd["opt_actor"]); ag.optimizer_critic.load_state_dict(sd["opt_critic"])
+        self.opponent.actor.load_state_dict(sd["opponent_actor"])
+        ag.sync_kernels(); self.opponent.sync_kernels()
+        return self
+
+
 def shard_bounds(n_total: int, world: int, rank: int):
     """contiguous env shard of rank: [lo, hi)"""
     per = n_total // world

@@ -464,3 +464,42 @@ def test_actor_fused_state_path_equals_observe_path(golden, eng):
     assert torch.equal(obs_out, xn)
     a_o, lp_o = actor.sample(obs=xn, eps_in=eps)
     assert torch.equal(a_f, a_o) and torch.equal(lp_f, lp_o)
+
+
+# ============================================================================ sharding / resume
+def test_env_shard_invariance_emulated_ranks(golden, eng):
+    """config 4 shape in miniature: splitting the env axis over ranks changes nothing per env (ranks emulated as
+    separate batches on one GPU; there is no cross-env term and no collective in the rollout)."""
+    g = golden("env_golden.npz")
+    n, T = 1024, 12
+    kw = dict(mode="rk4", substeps=7, h=1.0, d_capture=20000.0, max_episode_steps=5)
+    full = eng.EnvBatch(n, **kw)
+    shards = [eng.EnvBatch(n // 4, **kw) for _ in range(4)]
+    rng = np.random.default_rng(0)
+    for t in range(T):
+        pa = torch.from_numpy(rng.uniform(-2, 2, (n, 3)).astype(np.float32)).cuda()
+        ea = torch.from_numpy(rng.uniform(-2, 2, (n, 3)).astype(np.float32)).cuda()
+        r, d = full.step(pa, ea)
+        for k, sh in enumerate(shards):
+            lo, hi = k * n // 4, (k + 1) * n // 4
+            rs, ds = sh.step(pa[lo:hi].contiguous(), ea[lo:hi].contiguous())
+            assert torch.equal(rs, r[lo:hi]) and torch.equal(ds, d[lo:hi])
+            assert torch.equal(sh.state, full.state[:, lo:hi]) and torch.equal(sh.istate, full.istate[:, lo:hi])
+
+
+def test_env_checkpoint_resume_is_exact(eng):
+    n = 300
+    kw = dict(mode="cw", d_capture=20000.0, max_episode_steps=6)
+    a = eng.EnvBatch(n, **kw)
+    rng = np.random.default_rng(1)
+    acts = [(torch.from_numpy(rng.uniform(-2, 2, (n, 3)).astype(np.float32)).cuda(),
+             torch.from_numpy(rng.uniform(-2, 2, (n, 3)).astype(np.float32)).cuda()) for _ in range(10)]
+    for pa, ea in acts[:5]:
+        a.step(pa, ea)
+    sd = a.state_dict()
+    b = eng.EnvBatch(n, **kw).load_state_dict(sd)
+    for pa, ea in acts[5:]:
+        ra, da = a.step(pa, ea)
+        rb, db = b.step(pa, ea)
+        assert torch.equal(ra, rb) and torch.equal(da, db)
+    assert torch.equal(a.state, b.state) and torch.equal(a.istate, b.istate)
