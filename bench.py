@@ -378,7 +378,11 @@ def run_ours(args, rank, world, local_rank):
         "e2e": e2e,
         "roofline": {"kernel": "env_step_kernel<rk4> (fused impulse + 2x100 RK4+J2 substeps + terminal + danger zone + reward + stats)",
                      "bound": "fp64", "achieved": ach_env, "peak": peak64, "unit": "TFLOP/s", "frac": ach_env / peak64,
-                     "traffic": None, "peak_source": "DFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                     "traffic": 26.72e6 * (n / 65536.0), "traffic_unit": "bytes per env-step launch pair",
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum: env_front_rk4_kernel 9.97 MB + "
+                                       "env_step_kernel 11.39 + 5.35 MB at 65 536 envs (profiles/r01_ncu_kernels.txt), scaled by n; "
+                                       "algorithmic 345 B/env-step = 22.6 MB",
+                     "peak_source": "DFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                      "algorithmic_flops_per_env_step": FLOP_ENV_STEP * (S / 100.0), "launch_ms": t_env, "launch_ms_min": t_env_min,
                      "hbm_achieved_gbs": BYTES_ENV_STEP * n / (t_env * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak},
         "kernels": {
