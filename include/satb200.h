@@ -204,6 +204,13 @@ int sat_state_eq(const double* x, double* f, int64_t n, int64_t ld, double mu, d
 /* Clohessy_Wiltshire(...).State_transition_matrix(t) (satellite_function.py:753-781): x [6][ld] <- M x with
  * numpy's dgemv summation order; stm_host is the row-major 6x6 matrix in HOST memory (copied into the launch). */
 int sat_cw_propagate(double* x, int64_t n, int64_t ld, const double* stm_host, void* stream);
+/* Numerical_calculation_method(...).numerical_calculation(t) (satellite_function.py:783-839): the CW ODE (orbit_ode,
+ * :793-821, thrust = J2 = 0) integrated from 0 to t_bound by scipy's adaptive RK45 (Dormand-Prince 5(4), scipy 1.18.1
+ * step control restated), value at t_bound, for n states x [6][ld] in place. w2 = 2*omega, w3 = 3*omega**2,
+ * wz = omega**2 as python computes them; rtol/atol = solve_ivp's 1e-3 / 1e-6. status_out (nullable) [n]: 0, or -1
+ * where scipy would stop with "step size too small". */
+int sat_cw_ode_rk45(double* x, int64_t n, int64_t ld, double t_bound, double w2, double w3, double wz,
+                    double rtol, double atol, int32_t* status_out, void* stream);
 /* calculate_orbital_elements(miu, R0, V0) (satellite_function.py:161-255): rv [n][6] -> (a,e,i,omega,Omega,f) [n][6];
  * kind_out [n] = 6, or 0 for the circular / parabolic element sets (which this library does not produce). */
 int sat_orbital_elements(const double* rv, int64_t n, double miu, double* elements_out, int32_t* kind_out, void* stream);

@@ -63,6 +63,8 @@ def lib():
         L.orc_danger_zone.restype = i32
         L.orc_danger_zone_debug.argtypes = [dp, dp, dp, dp, C.c_double, C.c_double, dp]
         L.orc_danger_zone_debug.restype = i32
+        L.orc_cw_ode_rk45.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int)]
+        L.orc_cw_ode_rk45.restype = i32
         L.orc_env_init.argtypes = [C.POINTER(OrcEnv), C.c_double, C.c_double, C.c_double, C.c_double, i32]
         L.orc_env_reset.argtypes = [C.POINTER(OrcEnv), i32, dp]
         L.orc_env_step.argtypes = [C.POINTER(OrcEnv), dp, dp, dp, i32, dp, dp]
@@ -129,6 +131,23 @@ def cw_apply(M, s):
     out = np.empty(6)
     lib().orc_cw_apply(_dp(M), _dp(s), _dp(out))
     return out
+
+
+def cw_ode_constants():
+    """(2*omega, 3*omega**2, omega**2) exactly as orbit_ode computes them (satellite_function.py:796-801, 818-820)"""
+    import math
+    mu, r = 398600, 35786
+    omega = math.sqrt(mu / (r ** 3))
+    return 2 * omega, 3 * omega ** 2, omega ** 2
+
+
+def cw_ode_rk45(y0, t):
+    y = _f64(y0).copy()
+    w2, w3, wz = cw_ode_constants()
+    ns = C.c_int()
+    rc = lib().orc_cw_ode_rk45(_dp(y), float(t), w2, w3, wz, C.byref(ns))
+    assert rc == 0
+    return y, ns.value
 
 
 # ------------------------------------------------------------------ elements / danger zone

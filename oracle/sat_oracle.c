@@ -712,3 +712,106 @@ void orc_gaussian_sample(const float* mean, const float* log_std, const float* e
             a[i * act_dim + j] = x; logp[i * act_dim + j] = lp;
         }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Numerical_calculation_method.orbit_ode / numerical_calculation, satellite_function.py:793-839:
+ * scipy.integrate.solve_ivp(method="RK45", rtol=1e-3, atol=1e-6, t_eval=arange(0, t+50, 50)) on the CW ODE,
+ * value at the last t_eval point (= t_bound). Restates scipy 1.18.1's RungeKutta._step_impl, select_initial_step
+ * and RkDenseOutput (third-party, Dormand-Prince 5(4)); w2 = 2*omega, w3 = 3*omega**2, wz = omega**2 are computed
+ * by the caller exactly as python does (:801, :818-820). Thrust and J2 terms are identically zero there.
+ * ------------------------------------------------------------------------------------------ */
+static void cw_rhs(const double X[6], double w2, double w3, double wz, double f[6]) {
+    f[0] = X[3]; f[1] = X[4]; f[2] = X[5];
+    f[3] = ((w2 * X[4] + w3 * X[0]) + 0.0) + 0.0;           /* :818 */
+    f[4] = ((-w2) * X[3] + 0.0) + 0.0;                      /* :819 */
+    f[5] = ((-wz) * X[2] + 0.0) + 0.0;                      /* :820 */
+}
+static double rms6(const double x[6]) {
+    double s = 0; int k;
+    for (k = 0; k < 6; ++k) s += x[k] * x[k];
+    return sqrt(s) / sqrt(6.0);
+}
+static const double RK45_A[6][5] = {{0, 0, 0, 0, 0}, {0.2, 0, 0, 0, 0}, {0.075, 0.225, 0, 0, 0},
+    {0.9777777777777777, -3.7333333333333334, 3.5555555555555554, 0, 0},
+    {2.9525986892242035, -11.595793324188385, 9.822892851699436, -0.2908093278463649, 0},
+    {2.8462752525252526, -10.757575757575758, 8.906422717743473, 0.2784090909090909, -0.2735313036020583}};
+static const double RK45_B[6] = {0.09114583333333333, 0.0, 0.44923629829290207, 0.6510416666666666, -0.322376179245283, 0.13095238095238096};
+static const double RK45_E[7] = {-0.0012326388888888888, 0.0, 0.0042527702905061394, -0.03697916666666667, 0.05086379716981132, -0.0419047619047619, 0.025};
+static const double RK45_P[7][4] = {{1.0, -2.8535800653862835, 3.0717434641059005, -1.1270175653862835}, {0, 0, 0, 0},
+    {0.0, 4.023133379230305, -6.249321565289, 2.675424484351598}, {0.0, -3.7324019615885042, 10.068970589843675, -5.685526961588504},
+    {0.0, 2.5548038301849423, -6.399112377351017, 3.5219323679207912}, {0.0, -1.3744241142186024, 3.272657752246729, -1.7672812570757455},
+    {0.0, 1.3824689317781436, -3.764937863556287, 2.382468931778144}};
+
+int orc_cw_ode_rk45(double y[6], double t_bound, double w2, double w3, double wz, int* nsteps_out) {
+    const double rtol = 1e-3, atol = 1e-6, SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0, err_exp = -0.2;
+    double t = 0.0, f[6], K[7][6], y_new[6], f_new[6], y_old[6], scale[6], tmp[6], h_abs, h = 0.0;
+    int k, s, j, nsteps = 0;
+    cw_rhs(y, w2, w3, wz, f);
+    {   /* select_initial_step */
+        double d0, d1, d2, h0, h1, y1[6], f1[6];
+        for (k = 0; k < 6; ++k) scale[k] = atol + fabs(y[k]) * rtol;
+        for (k = 0; k < 6; ++k) tmp[k] = y[k] / scale[k];
+        d0 = rms6(tmp);
+        for (k = 0; k < 6; ++k) tmp[k] = f[k] / scale[k];
+        d1 = rms6(tmp);
+        h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, fabs(t_bound));
+        for (k = 0; k < 6; ++k) y1[k] = y[k] + h0 * 1.0 * f[k];
+        cw_rhs(y1, w2, w3, wz, f1);
+        for (k = 0; k < 6; ++k) tmp[k] = (f1[k] - f[k]) / scale[k];
+        d2 = rms6(tmp) / h0;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+        else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+        h_abs = fmin(fmin(100 * h0, h1), fabs(t_bound));
+    }
+    while (t != t_bound) {                                   /* OdeSolver.step until finished */
+        double min_step = 10 * fabs(nextafter(t, INFINITY) - t), t_new = t, error_norm;
+        int accepted = 0, rejected = 0;
+        if (h_abs < min_step) h_abs = min_step;
+        while (!accepted) {
+            if (h_abs < min_step) return -1;                 /* TOO_SMALL_STEP */
+            h = h_abs; t_new = t + h;
+            if (t_new - t_bound > 0) t_new = t_bound;
+            h = t_new - t; h_abs = fabs(h);
+            for (k = 0; k < 6; ++k) K[0][k] = f[k];           /* rk_step */
+            for (s = 1; s < 6; ++s) {
+                double ys[6];
+                for (k = 0; k < 6; ++k) {
+                    double dy = 0;
+                    for (j = 0; j < s; ++j) dy += K[j][k] * RK45_A[s][j];
+                    ys[k] = y[k] + dy * h;
+                }
+                cw_rhs(ys, w2, w3, wz, K[s]);
+            }
+            for (k = 0; k < 6; ++k) {
+                double acc = 0;
+                for (j = 0; j < 6; ++j) acc += K[j][k] * RK45_B[j];
+                y_new[k] = y[k] + h * acc;
+            }
+            cw_rhs(y_new, w2, w3, wz, f_new);
+            for (k = 0; k < 6; ++k) K[6][k] = f_new[k];
+            for (k = 0; k < 6; ++k) {
+                double e = 0;
+                for (j = 0; j < 7; ++j) e += K[j][k] * RK45_E[j];
+                scale[k] = atol + fmax(fabs(y[k]), fabs(y_new[k])) * rtol;
+                tmp[k] = (e * h) / scale[k];
+            }
+            error_norm = rms6(tmp);
+            if (error_norm < 1) {
+                double factor = (error_norm == 0) ? MAX_FACTOR : fmin(MAX_FACTOR, SAFETY * pow(error_norm, err_exp));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor; accepted = 1;
+            } else { h_abs *= fmax(MIN_FACTOR, SAFETY * pow(error_norm, err_exp)); rejected = 1; }
+        }
+        for (k = 0; k < 6; ++k) { y_old[k] = y[k]; y[k] = y_new[k]; f[k] = f_new[k]; }
+        t = t_new; ++nsteps;
+    }
+    /* value at t_eval[-1] == t_bound comes from the dense output of the last step at x = 1 (ivp.py) */
+    for (k = 0; k < 6; ++k) {
+        double q = 0;
+        for (j = 0; j < 4; ++j) { double c = 0; for (s = 0; s < 7; ++s) c += K[s][k] * RK45_P[s][j]; q += c; }
+        y[k] = h * q + y_old[k];
+    }
+    if (nsteps_out) *nsteps_out = nsteps;
+    return 0;
+}

@@ -94,6 +94,10 @@ void orc_env_step_rk4_batch(orc_env* envs, int32_t* counts, int64_t n, double h,
                             double mu, double re, double j2, const double* pa, const double* ea,
                             double* obs, double* reward, uint8_t* done, int auto_reset, int nthreads);
 
+/* ---- Numerical_calculation_method.numerical_calculation (satellite_function.py:793-839): scipy RK45 on the CW ODE;
+ * y in/out, returns 0 or -1 (step too small) ---- */
+int orc_cw_ode_rk45(double y[6], double t_bound, double w2, double w3, double wz, int* nsteps_out);
+
 /* ---- normalisation (normalization.py:7-63) ---- */
 typedef struct { int64_t n; int dim; double* mean; double* S; double* std; } orc_rms;
 void orc_rms_update(orc_rms* r, const double* x);                       /* :19-29 incl. n==1 rule */

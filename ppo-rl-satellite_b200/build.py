@@ -26,6 +26,7 @@ UNITS = {
     "rk4.cu": ["-fmad=false"],
     "env_step.cu": ["-fmad=false"],
     "gae.cu": ["-fmad=false"],
+    "cw_ode.cu": ["-fmad=false"],
     "actor.cu": [],
     "capi.cu": [],
 }

@@ -2,8 +2,9 @@
 
 Clohessy_Wiltshire.State_transition_matrix, Time_window_of_danger_zone.{calculate_orbital_elements,
 calculate_state_information, calculate_number_of_hanger_area} run as CUDA kernels (batch of one, or batched when
-given arrays with a leading axis). Out of scope (never called by the env or the driver): the
-time-window sweep, Lagrange propagation, Danger_index_and_TW_matching_index, Numerical_calculation_method.
+given arrays with a leading axis). Numerical_calculation_method.numerical_calculation (the RK45 propagator the env has
+commented out) is a per-state adaptive kernel. Out of scope (never called by the env or the driver): the
+time-window sweep, Lagrange propagation, Danger_index_and_TW_matching_index.
 """
 import numpy as np
 
@@ -100,6 +101,38 @@ class Time_window_of_danger_zone:
             raise AttributeError("circular / parabolic element set: the reference raises here as well")
         self.num_td = n
         return n
+
+
+class Numerical_calculation_method:
+    """satellite_function.py:783-839: RK45 (scipy solve_ivp semantics) on the CW ODE for both craft."""
+
+    def __init__(self, R0_c=None, V0_c=None, R0_t=None, V0_t=None):
+        self.R0_c, self.V0_c, self.R0_t, self.V0_t = R0_c, V0_c, R0_t, V0_t
+        self.u = 3.986e5
+        self.pursuer_initial_state = np.concatenate((self.R0_c, self.V0_c))
+        self.escaper_initial_state = np.concatenate((self.R0_t, self.V0_t))
+
+    @staticmethod
+    def _constants():
+        import math
+        mu, r = 398600, 35786                                  # :796,799 (python ints: r ** 3 is exact)
+        omega = math.sqrt(mu / (r ** 3))                       # :801
+        return 2 * omega, 3 * omega ** 2, omega ** 2           # :818-820
+
+    def numerical_calculation(self, t):
+        import torch
+        if t <= 0 or t % 50 != 0:
+            raise ValueError("Values in `t_eval` are not within `t_span`.")     # what solve_ivp raises for arange(0, t+50, 50)
+        w2, w3, wz = self._constants()
+        x, _buf = _eng.alloc_soa(6, 2, torch.float64, "cuda")
+        x[:, 0] = _dev(self.pursuer_initial_state)
+        x[:, 1] = _dev(self.escaper_initial_state)
+        _L.check(_L.load().sat_cw_ode_rk45(x.data_ptr(), 2, x.stride(0), float(t), w2, w3, wz, 1e-3, 1e-6, None,
+                                           _L.stream_ptr()), "sat_cw_ode_rk45")
+        out = x.cpu().numpy()
+        self.R0_c, self.V0_c = out[:3, 0].copy(), out[3:, 0].copy()
+        self.R0_t, self.V0_t = out[:3, 1].copy(), out[3:, 1].copy()
+        return out[:, 0].copy(), out[:, 1].copy()
 
 
 def orbital_elements_batch(miu, rv):

@@ -302,11 +302,29 @@ def gen_norm():
          rs_final_std=np.asarray(rs.running_ms.std, dtype=np.float64))
 
 
+def gen_ode():
+    """Numerical_calculation_method.numerical_calculation (scipy RK45 on the CW ODE), satellite_function.py:783-839"""
+    sf = refshim.load()["satellite_function"]
+    rng = np.random.default_rng(21)
+    n = 240
+    sc = np.where((np.arange(n) % 2 == 0)[:, None], np.concatenate([rng.normal(0, 2e5, (n, 3)), rng.normal(0, 3, (n, 3))], axis=1),
+                  np.concatenate([rng.normal(0, 100, (n, 3)), rng.normal(0, 0.01, (n, 3))], axis=1))
+    st = np.concatenate([rng.normal(0, 5e4, (n, 3)), rng.normal(0, 2, (n, 3))], axis=1)
+    ts = np.array([100, 600, 50, 1000] * (n // 4), dtype=np.float64)
+    oc, ot = [], []
+    for k in range(n):
+        a, b = sf.Numerical_calculation_method(R0_c=sc[k, :3].copy(), V0_c=sc[k, 3:].copy(), R0_t=st[k, :3].copy(),
+                                               V0_t=st[k, 3:].copy()).numerical_calculation(int(ts[k]))
+        oc.append(a); ot.append(b)
+    save("ode_golden.npz", state_c=sc, state_t=st, t=ts, out_c=np.array(oc), out_t=np.array(ot))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rk4", "elements", "env", "danger", "ppo", "norm"]
+    which = sys.argv[1:] or ["rk4", "elements", "env", "danger", "ppo", "norm", "ode"]
     if "rk4" in which: gen_rk4()
     if "elements" in which: gen_elements()
     if "env" in which: gen_env()
     if "danger" in which: gen_fsolve_dz()
     if "ppo" in which: gen_ppo()
     if "norm" in which: gen_norm()
+    if "ode" in which: gen_ode()

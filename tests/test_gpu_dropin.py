@@ -208,3 +208,16 @@ def test_vector_trainer_collect_and_update(oracle, mods, tmp_path):
     tr.update(mini_batch_size=1024)
     assert any(not torch.equal(b, p.detach()) for b, p in zip(before, agent.critic.parameters()))
     assert tr.obs_stats.n == n * (T + 1)
+
+
+def test_numerical_calculation_method_rk45(golden, mods):
+    """the RK45 propagator the env has commented out (environment.py:123-128), scipy solve_ivp semantics"""
+    g = golden("ode_golden.npz")
+    for k in range(0, len(g["t"]), 3):
+        obj = mods.sf.Numerical_calculation_method(R0_c=g["state_c"][k, :3].copy(), V0_c=g["state_c"][k, 3:].copy(),
+                                                   R0_t=g["state_t"][k, :3].copy(), V0_t=g["state_t"][k, 3:].copy())
+        a, b = obj.numerical_calculation(int(g["t"][k]))
+        np.testing.assert_allclose(a, g["out_c"][k], rtol=2e-12, atol=1e-9)
+        np.testing.assert_allclose(b, g["out_t"][k], rtol=2e-12, atol=1e-9)
+    with pytest.raises(ValueError):
+        obj.numerical_calculation(75)

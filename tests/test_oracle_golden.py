@@ -167,3 +167,13 @@ def test_actor_critic_forward(golden, oracle):
     np.testing.assert_allclose(lp, g["logp"], rtol=1e-5, atol=1e-5)
     v = oracle.critic_forward(Wc, g["obs"])
     np.testing.assert_allclose(v, g["value"], rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ Numerical_calculation_method (scipy RK45 on the CW ODE)
+def test_cw_ode_rk45_matches_reference(golden, oracle):
+    g = golden("ode_golden.npz")
+    for k in range(len(g["t"])):
+        for y0, ref in ((g["state_c"][k], g["out_c"][k]), (g["state_t"][k], g["out_t"][k])):
+            y, nsteps = oracle.cw_ode_rk45(y0, g["t"][k])
+            assert 2 <= nsteps <= 8
+            np.testing.assert_allclose(y, ref, rtol=2e-12, atol=1e-9)
