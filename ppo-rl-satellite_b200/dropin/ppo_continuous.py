@@ -114,8 +114,11 @@ class PPO_continuous:
         self.actor = Actor_Gaussian(args, agent_idx).to(self.device)
         self.critic = Critic(args, agent_idx).to(self.device)
         eps = dict(eps=1e-5) if self.set_adam_eps else {}
-        self.optimizer_actor = torch.optim.Adam(self.actor.parameters(), lr=self.lr_a, **eps)
-        self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=self.lr_c, **eps)
+        # capturable Adam with a device-resident learning rate: the whole optimiser step can live in a CUDA graph
+        cap = dict(capturable=True) if self.device.type == "cuda" else {}
+        self.optimizer_actor = torch.optim.Adam(self.actor.parameters(), lr=torch.tensor(float(self.lr_a), device=self.device), **eps, **cap)
+        self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=torch.tensor(float(self.lr_c), device=self.device), **eps, **cap)
+        self._graph = None
         self._use_tanh = bool(args.use_tanh)
         self.actor_kernel = _eng.GaussianActorKernel(max_action=self.max_action, use_tanh=self._use_tanh, device=self.device)
         self.critic_kernel = _eng.GaussianActorKernel(use_tanh=self._use_tanh, device=self.device, critic=True)
@@ -162,44 +165,98 @@ class PPO_continuous:
         if self.use_lr_decay:
             self.lr_decay(total_steps)
 
-    def optimize(self, s, a, a_logprob, adv, v_target, mini_batch_size=None, group=None):
-        """K epochs of clipped-PPO minibatch steps (ppo_continuous.py:213-239) on device tensors."""
+    def _minibatch_step(self, s, a, a_logprob, adv, v_target, group):
+        """one clipped-PPO actor step + one critic step on a minibatch (ppo_continuous.py:216-239)"""
+        dist_now = self.actor.get_dist(s)
+        dist_entropy = dist_now.entropy().sum(1, keepdim=True)
+        a_logprob_now = dist_now.log_prob(a)
+        ratios = torch.exp(a_logprob_now.sum(1, keepdim=True) - a_logprob.sum(1, keepdim=True))
+        surr1 = ratios * adv
+        surr2 = torch.clamp(ratios, 1 - self.epsilon, 1 + self.epsilon) * adv
+        actor_loss = -torch.min(surr1, surr2) - self.entropy_coef * dist_entropy
+        self.optimizer_actor.zero_grad(set_to_none=False)
+        actor_loss.mean().backward()
+        allreduce_grads_(self.actor, group)
+        if self.use_grad_clip:
+            torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.5)
+        self.optimizer_actor.step()
+        v_s = self.critic(s)
+        critic_loss = F.mse_loss(v_target, v_s)
+        self.optimizer_critic.zero_grad(set_to_none=False)
+        critic_loss.backward()
+        allreduce_grads_(self.critic, group)
+        if self.use_grad_clip:
+            torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 0.5)
+        self.optimizer_critic.step()
+
+    def _graph_for(self, tensors, mb, group):
+        """CUDA graph of (gather minibatch by a static index buffer -> _minibatch_step), keyed by the buffer addresses"""
+        key = (tuple(t.data_ptr() for t in tensors), tuple(t.shape for t in tensors), mb)
+        if self._graph is not None and self._graph["key"] == key:
+            return self._graph
+        idx = torch.zeros(mb, dtype=torch.long, device=self.device)
+
+        def body():
+            self._minibatch_step(*(t.index_select(0, idx) for t in tensors), group)
+        # warm-up on a side stream (allocator, cuBLAS handles, Adam state), restoring the weights afterwards
+        saved = [p.detach().clone() for p in list(self.actor.parameters()) + list(self.critic.parameters())]
+        opt_saved = (self.optimizer_actor.state_dict(), self.optimizer_critic.state_dict())
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        with torch.no_grad():
+            for p, q in zip(list(self.actor.parameters()) + list(self.critic.parameters()), saved):
+                p.copy_(q)
+        import copy
+        self.optimizer_actor.load_state_dict(copy.deepcopy(opt_saved[0]))
+        self.optimizer_critic.load_state_dict(copy.deepcopy(opt_saved[1]))
+        self._graph = {"key": key, "graph": g, "idx": idx}
+        return self._graph
+
+    def optimize(self, s, a, a_logprob, adv, v_target, mini_batch_size=None, group=None, use_graph=False):
+        """K epochs of clipped-PPO minibatch steps (ppo_continuous.py:213-239) on device tensors.
+        use_graph: replay one captured CUDA graph per minibatch (static buffers, full minibatches only)."""
         B = s.shape[0]
         mb = mini_batch_size or self.mini_batch_size
+        tensors = (s, a, a_logprob, adv, v_target)
+        graph = None
+        if use_graph and B >= mb:
+            try:
+                graph = self._graph_for(tensors, mb, group)
+            except Exception as exc:                      # capture not possible here: stay eager, say so once
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the PPO step failed ({exc!r}); running eagerly")
+                graph = None
         for _ in range(self.K_epochs):
             perm = torch.randperm(B, device=s.device)
             for lo in range(0, B, mb):
                 index = perm[lo:lo + mb]
-                dist_now = self.actor.get_dist(s[index])
-                dist_entropy = dist_now.entropy().sum(1, keepdim=True)
-                a_logprob_now = dist_now.log_prob(a[index])
-                ratios = torch.exp(a_logprob_now.sum(1, keepdim=True) - a_logprob[index].sum(1, keepdim=True))
-                surr1 = ratios * adv[index]
-                surr2 = torch.clamp(ratios, 1 - self.epsilon, 1 + self.epsilon) * adv[index]
-                actor_loss = -torch.min(surr1, surr2) - self.entropy_coef * dist_entropy
-                self.optimizer_actor.zero_grad()
-                actor_loss.mean().backward()
-                allreduce_grads_(self.actor, group)
-                if self.use_grad_clip:
-                    torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.5)
-                self.optimizer_actor.step()
-                v_s = self.critic(s[index])
-                critic_loss = F.mse_loss(v_target[index], v_s)
-                self.optimizer_critic.zero_grad()
-                critic_loss.backward()
-                allreduce_grads_(self.critic, group)
-                if self.use_grad_clip:
-                    torch.nn.utils.clip_grad_norm_(self.critic.parameters(), 0.5)
-                self.optimizer_critic.step()
+                if graph is not None and index.numel() == mb:
+                    graph["idx"].copy_(index)
+                    graph["graph"].replay()
+                else:
+                    self._minibatch_step(*(t[index] for t in tensors), group)
         self._dirty = True
 
     def lr_decay(self, total_steps):
         lr_a_now = self.lr_a * (1 - total_steps / self.max_train_steps)
         lr_c_now = self.lr_c * (1 - total_steps / self.max_train_steps)
         for p in self.optimizer_actor.param_groups:
-            p['lr'] = lr_a_now
+            if torch.is_tensor(p['lr']):
+                p['lr'].fill_(lr_a_now)           # device-resident: visible to a captured graph
+            else:
+                p['lr'] = lr_a_now
         for p in self.optimizer_critic.param_groups:
-            p['lr'] = lr_c_now
+            if torch.is_tensor(p['lr']):
+                p['lr'].fill_(lr_c_now)
+            else:
+                p['lr'] = lr_c_now
 
     def save_checkpoint(self):
         self.actor.save_checkpoint()

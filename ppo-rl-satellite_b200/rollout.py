@@ -83,12 +83,12 @@ class VectorTrainer:
             eng.adv_normalize_(buf.adv, group=group)
         return buf.adv, buf.v_target
 
-    def update(self, mini_batch_size: int, total_steps: int = 0, group=None):
+    def update(self, mini_batch_size: int, total_steps: int = 0, group=None, use_graph: bool = True):
         buf, ag = self.buf, self.agent
         adv, v_target = self.compute_advantages(group)
         B = self.T * self.env.n
         ag.optimize(buf.obs[:self.T].reshape(B, 18), buf.act.reshape(B, 3), buf.logp.reshape(B, 3), adv.reshape(B, 1),
-                    v_target.reshape(B, 1), mini_batch_size=mini_batch_size, group=group)
+                    v_target.reshape(B, 1), mini_batch_size=mini_batch_size, group=group, use_graph=use_graph)
         if ag.use_lr_decay:
             ag.lr_decay(total_steps)
         ag.sync_kernels()

@@ -221,3 +221,23 @@ def test_numerical_calculation_method_rk45(golden, mods):
         np.testing.assert_allclose(b, g["out_t"][k], rtol=2e-12, atol=1e-9)
     with pytest.raises(ValueError):
         obj.numerical_calculation(75)
+
+
+def test_graphed_update_equals_eager(mods, tmp_path):
+    """the CUDA-graph replay of the optimiser step is the same computation as the eager step"""
+    from ppo_rl_satellite_b200 import engine as eng, rollout
+    n, T, mb = 256, 8, 512
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        args = ppo_args(tmp_path, K_epochs=2)
+        env = eng.EnvBatch(n, mode="cw", d_capture=20000.0, max_episode_steps=5, auto_reset=True)
+        agent, opp = mods.ppo.PPO_continuous(args, 'pursuer'), mods.ppo.PPO_continuous(args, 'evader')
+        tr = rollout.VectorTrainer(env, agent, opp, T)
+        tr.collect()
+        torch.manual_seed(1)                                   # same minibatch permutations
+        tr.update(mini_batch_size=mb, use_graph=use_graph)
+        assert (agent._graph is not None) == use_graph
+        results.append([p.detach().clone() for p in list(agent.actor.parameters()) + list(agent.critic.parameters())])
+    for a, b in zip(*results):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
