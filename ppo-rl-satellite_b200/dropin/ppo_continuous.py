@@ -50,7 +50,8 @@ class Actor_Gaussian(nn.Module):
 
     def get_dist(self, s):
         mean = self.forward(s)
-        return Normal(mean, torch.exp(self.log_std.expand_as(mean)))
+        # validate_args=False: the default argument check synchronises the stream (illegal inside a CUDA-graph capture)
+        return Normal(mean, torch.exp(self.log_std.expand_as(mean)), validate_args=False)
 
     def save_checkpoint(self):
         torch.save(self.state_dict(), self.chkpt_file)
@@ -198,9 +199,13 @@ class PPO_continuous:
 
         def body():
             self._minibatch_step(*(t.index_select(0, idx) for t in tensors), group)
-        # warm-up on a side stream (allocator, cuBLAS handles, Adam state), restoring the weights afterwards
-        saved = [p.detach().clone() for p in list(self.actor.parameters()) + list(self.critic.parameters())]
-        opt_saved = (self.optimizer_actor.state_dict(), self.optimizer_critic.state_dict())
+        # warm-up on a side stream (allocator, cuBLAS handles, lazily created Adam state), then capture; weights and
+        # optimiser state are restored IN PLACE afterwards so the captured addresses stay valid
+        params = list(self.actor.parameters()) + list(self.critic.parameters())
+        saved = [p.detach().clone() for p in params]
+        opts = (self.optimizer_actor, self.optimizer_critic)
+        opt_saved = [{p: {k: v.detach().clone() for k, v in st.items() if torch.is_tensor(v)} for p, st in o.state.items()}
+                     for o in opts]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -211,11 +216,16 @@ class PPO_continuous:
         with torch.cuda.graph(g):
             body()
         with torch.no_grad():
-            for p, q in zip(list(self.actor.parameters()) + list(self.critic.parameters()), saved):
+            for p, q in zip(params, saved):
                 p.copy_(q)
-        import copy
-        self.optimizer_actor.load_state_dict(copy.deepcopy(opt_saved[0]))
-        self.optimizer_critic.load_state_dict(copy.deepcopy(opt_saved[1]))
+            for o, snap in zip(opts, opt_saved):
+                for p, st in o.state.items():
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            if p in snap and k in snap[p]:
+                                v.copy_(snap[p][k])
+                            else:
+                                v.zero_()             # state created during the warm-up: back to a fresh optimiser
         self._graph = {"key": key, "graph": g, "idx": idx}
         return self._graph
 
