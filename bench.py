@@ -264,7 +264,7 @@ def run_ours(args, rank, world, local_rank):
         k = t % RING
         env.step(rnd_pa[k], rnd_ea[k], obs_f32=buf_obs[k], reward=buf_rew[k], done=buf_done[k], obs_stats=obs_stats,
                  ret_stats=ret_stats, ret_std_out=buf_rstd[k:k + 1])
-    LAUNCHES_PER_STEP = 2   # env step kernel + statistics merge kernel
+    LAUNCHES_PER_STEP = 3   # env_front_rk4_kernel + env_step_kernel + stats_merge_kernel
 
     def barrier():
         if world > 1:

@@ -503,3 +503,61 @@ def test_env_checkpoint_resume_is_exact(eng):
         rb, db = b.step(pa, ea)
         assert torch.equal(ra, rb) and torch.equal(da, db)
     assert torch.equal(a.state, b.state) and torch.equal(a.istate, b.istate)
+
+
+# ============================================================================ BASELINE full sizes: size-independent properties
+def test_full_size_rk4_conservation_and_time_reversal(eng):
+    """1 048 576 random LEO/GEO states (config 4 size) x 1000 steps: energy and angular momentum are conserved with J2
+    off, and integrating back with -h returns to the start (RK4 is not symmetric: the residual is its truncation error)."""
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = torch.where(torch.arange(n, device="cuda") % 2 == 0, 6778.0 + 600.0 * torch.rand(n, generator=g, device="cuda", dtype=torch.float64),
+                    42164.0 + 100.0 * (torch.rand(n, generator=g, device="cuda", dtype=torch.float64) - 0.5))
+    ang = 6.283185307179586 * torch.rand(n, generator=g, device="cuda", dtype=torch.float64)
+    inc = 1.5 * torch.rand(n, generator=g, device="cuda", dtype=torch.float64)
+    v = torch.sqrt(398600.0 / r) * (1.0 + 0.01 * (torch.rand(n, generator=g, device="cuda", dtype=torch.float64) - 0.5))
+    x, _ = eng.alloc_soa(6, n, torch.float64, "cuda")
+    x[0], x[1], x[2] = r * torch.cos(ang), r * torch.sin(ang) * torch.cos(inc), r * torch.sin(ang) * torch.sin(inc)
+    x[3], x[4], x[5] = -v * torch.sin(ang), v * torch.cos(ang) * torch.cos(inc), v * torch.cos(ang) * torch.sin(inc)
+    x0 = x.clone()
+
+    def energy(s):
+        return 0.5 * (s[3:] ** 2).sum(0) - 398600.0 / torch.linalg.norm(s[:3], dim=0)
+
+    def hvec(s):
+        return torch.linalg.cross(s[:3].T, s[3:].T)
+    eng.rk4_propagate(x, 1.0, 1000, j2=0.0)
+    assert float((energy(x) / energy(x0) - 1).abs().max()) < 1e-10
+    assert float((torch.linalg.norm(hvec(x) - hvec(x0), dim=1) / torch.linalg.norm(hvec(x0), dim=1)).max()) < 1e-12
+    eng.rk4_propagate(x, -1.0, 1000, j2=0.0)
+    back = float((torch.linalg.norm(x[:3] - x0[:3], dim=0) / torch.linalg.norm(x0[:3], dim=0)).max())
+    assert back < 1e-9, back
+    # with J2 on, the z component of angular momentum is still conserved (axial symmetry)
+    eng.rk4_propagate(x, 1.0, 1000)
+    assert float(((hvec(x)[:, 2] - hvec(x0)[:, 2]).abs() / torch.linalg.norm(hvec(x0), dim=1)).max()) < 1e-9
+
+
+def test_full_size_env_batch_subset_vs_oracle(golden, oracle, eng):
+    """config 3 size (65 536 envs, cw mode): a random subset of 1024 envs is stepped by the oracle with the same actions and
+    must agree bit for bit (envs are independent; danger-zone flips excluded as in the batched test)."""
+    g = golden("env_golden.npz")
+    n, m, T = 65536, 1024, 24
+    kw = dict(d_capture=181200.0, max_episode_steps=10)
+    env = eng.EnvBatch(n, mode="cw", auto_reset=True, stm=g["stm100_columns"], **kw)
+    rng = np.random.default_rng(7)
+    sub = np.sort(rng.choice(n, m, replace=False))
+    orc = _oracle_batch(oracle, m, M=g["stm100_columns"], **kw)
+    obs = torch.empty((n, 18), dtype=torch.float64, device="cuda")
+    flipped = np.zeros(m, dtype=bool)
+    for t in range(T):
+        pa = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+        ea = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+        r, d = env.step(torch.from_numpy(pa).cuda(), torch.from_numpy(ea).cuda(), obs_f64=obs)
+        o_obs, o_r, o_d = orc.step(pa[sub].astype(np.float64), ea[sub].astype(np.float64))
+        flipped |= env.dangerous_zone.cpu().numpy()[sub] != orc.aux()[3]
+        ok = ~flipped
+        assert np.array_equal(d.cpu().numpy()[sub][ok], o_d[ok])
+        assert np.array_equal(r.cpu().numpy()[sub][ok], o_r[ok])
+        assert np.array_equal(obs.cpu().numpy()[sub][ok], o_obs[ok])
+    assert flipped.sum() <= 3
+    assert int(env.err.sum()) == 0 and int(env.done.sum()) >= 0
