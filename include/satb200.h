@@ -126,12 +126,14 @@ int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const in
 int sat_danger_zone_count(const double* rv, const double* dv, int64_t n, double u_grav, int32_t* count_out,
                           double* debug_out, void* stream);
 
-/* host-buffer form of step(): actions from host memory, obs_f32/reward/done to host memory.
- * d_io is a caller-provided device staging buffer of sat_env_step_host_bytes(n) bytes. */
+/* host-buffer form of step(): actions from (pinned) host memory, obs_f32/reward/done to host memory, synchronised
+ * before returning. d_io is a caller-provided device staging buffer of sat_env_step_host_bytes(n) bytes.
+ * With aux_stream != NULL and chunks > 1 (<= 16) the batch is cut into env ranges that alternate between `stream` and
+ * `aux_stream`, so the H2D copies, the kernels and the D2H copies of different ranges overlap. */
 int64_t sat_env_step_host_bytes(int64_t n);
 int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* ea_host,
                       float* obs_host, double* reward_host, uint8_t* done_host, void* d_io,
-                      const SatEnvParams* p, void* stream);
+                      const SatEnvParams* p, void* stream, void* aux_stream, int chunks);
 
 /* ------------------------------------------------------------------------------------------------
  * Normalisation. Replaces RunningMeanStd.update / Normalization.__call__ (normalization.py:19-43)

@@ -64,7 +64,7 @@ SIGNATURES = {
                                C.POINTER(SatEnvParams), _P]),
     "sat_danger_zone_count": (C.c_int, [_P, _P, _I64, _D, _P, _P, _P]),
     "sat_env_step_host_bytes": (_I64, [_I64]),
-    "sat_env_step_host": (C.c_int, [C.POINTER(SatEnvState), _P, _P, _P, _P, _P, _P, C.POINTER(SatEnvParams), _P]),
+    "sat_env_step_host": (C.c_int, [C.POINTER(SatEnvState), _P, _P, _P, _P, _P, _P, C.POINTER(SatEnvParams), _P, _P, _I32]),
     "sat_norm_update": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P]),
     "sat_actor_pack": (C.c_int, [C.POINTER(SatActorWeights), _P, _P]),
     "sat_actor_sample": (C.c_int, [C.POINTER(SatActorWeights), _P, C.POINTER(SatEnvState), _P, _I64, _I64,

@@ -746,16 +746,17 @@ int64_t sat_env_step_host_bytes(int64_t n) {
     if (n <= 0) return 0;
     // pa | ea (fp32 [n][3] each) | obs fp32 [n][18] | reward fp64 [n] | done u8 [n], each 256-byte aligned
     auto al = [](int64_t b) { return (b + 255) / 256 * 256; };
-    return al(n * 12) * 2 + al(n * 72) + al(n * 8) + al(n) + sat_workspace_bytes(n);
+    // + one workspace per env range for up to 16 ranges
+    return al(n * 12) * 2 + al(n * 72) + al(n * 8) + al(n) + sat_workspace_bytes(n) + 16 * sat_workspace_bytes(64) + 16 * 4096;
 }
 
 int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* ea_host,
                       float* obs_host, double* reward_host, uint8_t* done_host, void* d_io,
-                      const SatEnvParams* p, void* stream) {
+                      const SatEnvParams* p, void* stream, void* aux_stream, int chunks) {
     int rc = check_state(st);
     if (rc) return rc;
     if (!pa_host || !ea_host || !obs_host || !reward_host || !done_host || !d_io || !p) return SAT_ERR_NULL;
-    cudaStream_t s = (cudaStream_t)stream;
+    cudaStream_t s0 = (cudaStream_t)stream, s1 = (cudaStream_t)aux_stream;
     const int64_t n = st->n;
     auto al = [](int64_t b) { return (b + 255) / 256 * 256; };
     char* base = (char*)d_io;
@@ -764,19 +765,40 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
     float* d_obs = (float*)(base + 2 * al(n * 12));
     double* d_rew = (double*)(base + 2 * al(n * 12) + al(n * 72));
     uint8_t* d_done = (uint8_t*)(base + 2 * al(n * 12) + al(n * 72) + al(n * 8));
-    void* d_ws = (void*)(base + 2 * al(n * 12) + al(n * 72) + al(n * 8) + al(n));
-    cudaError_t ce;
-    if ((ce = cudaMemcpyAsync(d_pa, pa_host, n * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)ce;
-    if ((ce = cudaMemcpyAsync(d_ea, ea_host, n * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)ce;
+    char* d_ws = base + 2 * al(n * 12) + al(n * 72) + al(n * 8) + al(n);
     SatEnvParams q = *p;
     q.action_dtype = SAT_ACT_F32;
-    rc = sat_env_step(st, d_pa, d_ea, nullptr, d_obs, nullptr, nullptr, d_rew, d_done, nullptr, nullptr, nullptr,
-                      d_ws, &q, stream);
-    if (rc) return rc;
-    if ((ce = cudaMemcpyAsync(obs_host, d_obs, n * 72, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
-    if ((ce = cudaMemcpyAsync(reward_host, d_rew, n * 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
-    if ((ce = cudaMemcpyAsync(done_host, d_done, n, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
-    if ((ce = cudaStreamSynchronize(s)) != cudaSuccess) return (int)ce;
+    // env ranges of a multiple of 64 envs (keeps every sub-column 16-byte aligned), alternating between the two
+    // streams so that the H2D of the actions, the kernels and the D2H of the results of different ranges overlap
+    if (chunks < 1 || !s1) chunks = 1;
+    int64_t per = ((n + chunks - 1) / chunks + 63) / 64 * 64;
+    cudaError_t ce;
+    cudaEvent_t fork = nullptr;
+    if (chunks > 1) {
+        if ((ce = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return (int)ce;
+        cudaEventRecord(fork, s0);
+        cudaStreamWaitEvent(s1, fork, 0);
+    }
+    const int64_t ws_per = sat_workspace_bytes(per);
+    int k = 0;
+    for (int64_t lo = 0; lo < n; lo += per, ++k) {
+        const int64_t m = (n - lo < per) ? n - lo : per;
+        cudaStream_t s = (k & 1) ? s1 : s0;
+        SatEnvState sub = {st->state + lo, st->istate + lo, m, st->ld};
+        if ((ce = cudaMemcpyAsync(d_pa + lo * 3, pa_host + lo * 3, m * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)ce;
+        if ((ce = cudaMemcpyAsync(d_ea + lo * 3, ea_host + lo * 3, m * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)ce;
+        rc = sat_env_step(&sub, d_pa + lo * 3, d_ea + lo * 3, nullptr, d_obs + lo * 18, nullptr, nullptr, d_rew + lo,
+                          d_done + lo, nullptr, nullptr, nullptr, d_ws + (int64_t)k * ws_per, &q, (void*)s);
+        if (rc) return rc;
+        if ((ce = cudaMemcpyAsync(obs_host + lo * 18, d_obs + lo * 18, m * 72, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
+        if ((ce = cudaMemcpyAsync(reward_host + lo, d_rew + lo, m * 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
+        if ((ce = cudaMemcpyAsync(done_host + lo, d_done + lo, m, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
+    }
+    if ((ce = cudaStreamSynchronize(s0)) != cudaSuccess) return (int)ce;
+    if (chunks > 1) {
+        if ((ce = cudaStreamSynchronize(s1)) != cudaSuccess) return (int)ce;
+        cudaEventDestroy(fork);
+    }
     return SAT_OK;
 }
 

@@ -222,7 +222,9 @@ class EnvBatch:
         return reward, done
 
     # -- host-buffer form: the reference-facing call with numpy in / numpy out (e2e path)
-    def step_host(self, pa_np: np.ndarray, ea_np: np.ndarray):
+    def host_buffers(self):
+        """pinned host arrays (pa, ea, obs, reward, done). Filling pa/ea in place and passing them to step_host()
+        avoids the staging memcpy; obs/reward/done are overwritten by every step_host() call."""
         torch = self.torch
         if self._host is None:
             n = self.n
@@ -232,15 +234,35 @@ class EnvBatch:
                 obs=torch.empty((n, OBS_DIM), dtype=torch.float32).pin_memory(),
                 rew=torch.empty(n, dtype=torch.float64).pin_memory(),
                 done=torch.empty(n, dtype=torch.uint8).pin_memory(),
-                dio=torch.empty(self.lib.sat_env_step_host_bytes(n), dtype=torch.uint8, device=self.device))
+                dio=torch.zeros(self.lib.sat_env_step_host_bytes(n), dtype=torch.uint8, device=self.device),
+                streams=[torch.cuda.Stream(device=self.device)])
+            hb = self._host
+            hb["np"] = tuple(hb[k].numpy() for k in ("pa", "ea", "obs", "rew", "done"))
+        return self._host["np"]
+
+    def step_host(self, pa_np: np.ndarray, ea_np: np.ndarray, chunks: int = 2):
+        """step(pa, ea) with HOST arrays in and out: one sat_env_step_host call. With chunks > 1 the batch is cut into env
+        ranges pipelined over two CUDA streams inside the library (H2D of the actions, the env-step kernels and the D2H of
+        obs fp32 / reward / done of different ranges overlap). Measured at 65 536 envs (rk4 mode, PCIe 54 GB/s): chunks
+        {1: 333, 2: 327, 4: 405, 8: 566} us/step -- the latency-bound finish kernel does not shrink linearly with the range,
+        so two ranges is the optimum. Returns pinned numpy views (valid until the next call)."""
+        pa_h, ea_h, obs_h, rew_h, done_h = self.host_buffers()
         hb = self._host
-        hb["pa"].numpy()[...] = pa_np
-        hb["ea"].numpy()[...] = ea_np
+        if pa_np is not pa_h:
+            pa_h[...] = pa_np
+        if ea_np is not ea_h:
+            ea_h[...] = ea_np
+        chunks = max(1, min(int(chunks), 16, self.n // 64 or 1))
         L.check(self.lib.sat_env_step_host(C.byref(self.st), hb["pa"].data_ptr(), hb["ea"].data_ptr(),
                                            hb["obs"].data_ptr(), hb["rew"].data_ptr(), hb["done"].data_ptr(),
-                                           hb["dio"].data_ptr(), C.byref(self.params), L.stream_ptr()),
+                                           hb["dio"].data_ptr(), C.byref(self.params), L.stream_ptr(),
+                                           hb["streams"][0].cuda_stream if chunks > 1 else None, chunks),
                 "sat_env_step_host")
-        return hb["obs"].numpy(), hb["rew"].numpy(), hb["done"].numpy()
+        return obs_h, rew_h, done_h
+
+    def step_host_single(self, pa_np: np.ndarray, ea_np: np.ndarray):
+        """unpipelined form (one env range, one stream)"""
+        return self.step_host(pa_np, ea_np, chunks=1)
 
     @property
     def h2d_bytes_per_step(self):
