@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_ENV_STEP = 34800.0        # 2 craft x 100 substeps x 174 FLOP (RK4 + J2), fp64
 FLOP_RK4_J2 = 174.0
+FP64_INSTR_RK4_J2 = 106.5      # DFMA+DMUL+DADD per RK4+J2 step in the SASS of rk4_kernel<true,2> (cuobjdump)
 FLOP_ACTOR = 141824.0          # fp32 per actor forward
 BYTES_ENV_STEP = 345.0
 
@@ -393,6 +394,8 @@ def run_ours(args, rank, world, local_rank):
         "kernels": {
             "rk4_kernel (K1, 2^20 states x 100 substeps, J2)": {"ms": t_k1, "bound": "fp64", "achieved_tflops": ach_k1,
                                                               "frac_of_measured_fp64_peak": ach_k1 / peak64,
+                                                              "fp64_instr_per_rk4_step": FP64_INSTR_RK4_J2,
+                                                              "fp64_pipe_util_vs_measured_dfma_rate": (100 * nk1 / (t_k1 * 1e-3)) * FP64_INSTR_RK4_J2 / (peak64 * 1e12 / 2),
                                                               "rk4_steps_per_sec": 100 * nk1 / (t_k1 * 1e-3)},
             "actor_kernel (K3, one actor)": {"ms": t_act, "bound": "fp32", "achieved_tflops": ach_act,
                                              "frac_of_measured_fp32_peak": ach_act / peak32},

@@ -5,7 +5,7 @@
 //       OpenBLAS calls perform (ddot, dnrm2-as-sqrt(dot), dgemv, cross, scalar +-*/), written with
 //       explicit __dmul_rn/__dadd_rn/__fma_rn so no compiler flag can re-associate or fuse them;
 //   (2) the RK4 propagator core, written with explicit fma() for minimum FP64-pipe instruction
-//       count (110 per RK4+J2 step), whose parity bar is 1e-9 relative, not bit identity.
+//       count (106 per RK4+J2 step), whose parity bar is 1e-9 relative, not bit identity.
 // Translation units that include this file are compiled with -fmad=false, so every fused
 // operation in the binary is one that is spelled fma() here.
 #pragma once
@@ -92,7 +92,7 @@ SAT_DEV double rsqrt_halley(double x) {
     return fma(y0, pe, y0);
 }
 
-// a(x)/(-mu): 20 FP64-pipe instructions with J2, 13 without
+// a(x)/(-mu): 19 FP64-pipe instructions with J2, 13 without
 template <bool J2>
 SAT_DEV void accel_scaled(double x, double y, double z, double cj, double& ax, double& ay, double& az) {
     double zz = z * z;
@@ -104,9 +104,9 @@ SAT_DEV void accel_scaled(double x, double y, double z, double cj, double& ax, d
         double c = cj * ri2;            // 1.5 J2 Re^2 / r^2
         double q = zz * ri2;            // (z/r)^2
         double t1 = fma(-5.0, q, 1.0);  // 1 - 5 (z/r)^2
-        double fxy = fma(c, t1, 1.0);
-        double fz = fma(2.0, c, fxy);   // 1 + c (3 - 5 (z/r)^2)
-        double kxy = ri3 * fxy, kz = ri3 * fz;
+        double g = ri3 * c;             // 1.5 J2 Re^2 / r^5
+        double kxy = fma(g, t1, ri3);   // r^-3 (1 + c (1 - 5 (z/r)^2))
+        double kz = fma(2.0, g, kxy);   // r^-3 (1 + c (3 - 5 (z/r)^2))
         ax = kxy * x; ay = kxy * y; az = kz * z;
     } else {
         ax = ri3 * x; ay = ri3 * y; az = ri3 * z;
