@@ -384,6 +384,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": e2e,
         "roofline": {"kernel": "env_step_kernel<rk4> (fused impulse + 2x100 RK4+J2 substeps + terminal + danger zone + reward + stats)",
                      "bound": "fp64", "achieved": ach_env, "peak": peak64, "unit": "TFLOP/s", "frac": ach_env / peak64,
+                     "peak_nominal": 148 * 64 * 2 * 1.965e9 / 1e12, "frac_of_nominal": ach_env / (148 * 64 * 2 * 1.965e9 / 1e12),
                      "traffic": 26.72e6 * (n / 65536.0), "traffic_unit": "bytes per env-step launch pair",
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum: env_front_rk4_kernel 9.97 MB + "
                                        "env_step_kernel 11.39 + 5.35 MB at 65 536 envs (profiles/r01_ncu_kernels.txt), scaled by n; "
