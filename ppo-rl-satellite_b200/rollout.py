@@ -119,6 +119,40 @@ class VectorTrainer:
         return self
 
 
+class SelfPlay:
+    """Alternating pursuer / evader training on one device-resident env batch: the batched counterpart of CPPO_main.py's
+    `Sign == 0` branch (train_pursuer_network with reset(0), :94-161, then train_evader_network with reset(1), :163-230).
+    The upstream evader trainer updates the *pursuer* agent with the evader's buffer (CPPO_main.py:215); here the evader
+    learns from its own rollouts, which is the evident intent."""
+
+    def __init__(self, env: eng.EnvBatch, pursuer, evader, T: int, mini_batch_size: int, rank: int = 0, seed: int = 0, **kw):
+        self.env, self.mb = env, mini_batch_size
+        self.trainers = {0: VectorTrainer(env, pursuer, evader, T, rank=rank, seed=seed, **kw),
+                         1: VectorTrainer(env, evader, pursuer, T, rank=rank, seed=seed + 1, **kw)}
+
+    def run_phase(self, flag: int, iterations: int, group=None, use_graph: bool = True, callback=None):
+        env, tr = self.env, self.trainers[flag]
+        env.reset(flag=flag)                                   # reset(Flag) for every env; fuel / dis / dz persist (Q2)
+        tr.learner_is_pursuer = flag == 0
+        out = []
+        for it in range(iterations):
+            tr.collect()
+            stats = {"flag": flag, "iteration": it, "mean_reward": float(tr.buf.rew64.mean()),
+                     "episodes_finished": int(tr.buf.done.sum())}
+            tr.update(self.mb, total_steps=it, group=group, use_graph=use_graph)
+            out.append(stats)
+            if callback is not None:
+                callback(stats)
+        return out
+
+    def run(self, rounds: int, iterations_per_phase: int, **kw):
+        log = []
+        for _ in range(rounds):
+            log += self.run_phase(0, iterations_per_phase, **kw)
+            log += self.run_phase(1, iterations_per_phase, **kw)
+        return log
+
+
 def shard_bounds(n_total: int, world: int, rank: int):
     """contiguous env shard of rank: [lo, hi)"""
     per = n_total // world

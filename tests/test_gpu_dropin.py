@@ -241,3 +241,22 @@ def test_graphed_update_equals_eager(mods, tmp_path):
         results.append([p.detach().clone() for p in list(agent.actor.parameters()) + list(agent.critic.parameters())])
     for a, b in zip(*results):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_self_play_alternates_learners(mods, tmp_path):
+    from ppo_rl_satellite_b200 import engine as eng, rollout
+    args = ppo_args(tmp_path, K_epochs=1)
+    env = eng.EnvBatch(256, mode="cw", d_capture=20000.0, max_episode_steps=6, auto_reset=True)
+    pursuer, evader = mods.ppo.PPO_continuous(args, 'pursuer'), mods.ppo.PPO_continuous(args, 'evader')
+    sp = rollout.SelfPlay(env, pursuer, evader, T=6, mini_batch_size=512)
+    p0 = [p.detach().clone() for p in pursuer.actor.parameters()]
+    e0 = [p.detach().clone() for p in evader.actor.parameters()]
+    log = sp.run_phase(0, 1, use_graph=False)
+    assert env.params.flag == 0 and log[0]["flag"] == 0
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(p0, pursuer.actor.parameters()))
+    assert all(torch.equal(a, b.detach()) for a, b in zip(e0, evader.actor.parameters()))       # opponent frozen
+    p1 = [p.detach().clone() for p in pursuer.actor.parameters()]
+    log = sp.run_phase(1, 1, use_graph=False)
+    assert env.params.flag == 1 and np.isfinite(log[0]["mean_reward"])
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(e0, evader.actor.parameters()))
+    assert all(torch.equal(a, b.detach()) for a, b in zip(p1, pursuer.actor.parameters()))
