@@ -59,7 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            defs = [f"-D{d}" for d in os.environ.get("SAT_NVCC_DEFINES", "").split() if d]     # tuning experiments only
+            cmd = [nvcc] + ARCH + COMMON + extra + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):

@@ -19,7 +19,12 @@
 namespace {
 
 constexpr int IN = 18, HID = 256, ACTP = 4;     // ACTP: padded head count (actor 3, critic 1)
-constexpr int M = 64, THREADS = 128, KT = 16, NSTAGE = 2;
+#ifndef SAT_ACTOR_RT
+#define SAT_ACTOR_RT 8
+#endif
+constexpr int RT = SAT_ACTOR_RT;                // rows of the tile per thread (8: 128 threads/CTA, 4: 256 threads/CTA)
+constexpr int M = 64, THREADS = 16 * (M / RT), KT = 16, NSTAGE = 2;
+static_assert(RT == 8 || RT == 4, "row tile");
 constexpr int H1_LD = M + 4;
 
 // packed weight buffer (floats)
@@ -79,13 +84,16 @@ __device__ __forceinline__ float activate(float x, int use_tanh) { return use_ta
 // The 8 x 16 tile is held as 8 x 8 float2 and updated with Blackwell's packed FFMA2 (fma.rn.f32x2): the same
 // IEEE fp32 FMAs, two per issue slot, which leaves issue bandwidth for the LDS/address instructions.
 template <int K>
-__device__ __forceinline__ void tile_fma(float2 (&acc)[8][8], const float* __restrict__ A, int lda,
+__device__ __forceinline__ void tile_fma(float2 (&acc)[RT][8], const float* __restrict__ A, int lda,
                                          const float* __restrict__ B, int ty, int tx) {
 #pragma unroll 2
     for (int k = 0; k < K; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(A + k * lda + ty * 8);
-        const float4 a1 = *reinterpret_cast<const float4*>(A + k * lda + ty * 8 + 4);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float a[RT];
+#pragma unroll
+        for (int i4 = 0; i4 < RT / 4; ++i4) {
+            const float4 av = *reinterpret_cast<const float4*>(A + k * lda + ty * RT + i4 * 4);
+            a[i4 * 4] = av.x; a[i4 * 4 + 1] = av.y; a[i4 * 4 + 2] = av.z; a[i4 * 4 + 3] = av.w;
+        }
         float2 b[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -93,7 +101,7 @@ __device__ __forceinline__ void tile_fma(float2 (&acc)[8][8], const float* __res
             b[c * 2] = make_float2(bv.x, bv.y); b[c * 2 + 1] = make_float2(bv.z, bv.w);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < RT; ++i) {
             const float2 ai = make_float2(a[i], a[i]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = __ffma2_rn(ai, b[j], acc[i][j]);
@@ -102,7 +110,7 @@ __device__ __forceinline__ void tile_fma(float2 (&acc)[8][8], const float* __res
 }
 
 // element (row i, local column c*4+q) of the packed accumulator tile
-__device__ __forceinline__ float acc_at(const float2 (&acc)[8][8], int i, int c, int q) {
+__device__ __forceinline__ float acc_at(const float2 (&acc)[RT][8], int i, int c, int q) {
     const float2 v = acc[i][c * 2 + (q >> 1)];
     return (q & 1) ? v.y : v.x;
 }
@@ -167,9 +175,9 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
     }
 
     // ---------------- layer 1: h1 = act(W1 x + b1) -> h1T
-    float2 acc[8][8];
+    float2 acc[RT][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
     mbar_wait(&sm.bar_misc, 0);
@@ -180,13 +188,13 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
         for (int q = 0; q < 4; ++q) {
             const int j = c * 64 + tx * 4 + q;
             const float bias = __ldg(packed + OFF_B1 + j);
-            float4 lo, hi;
-            lo.x = activate(acc_at(acc, 0, c, q) + bias, use_tanh); lo.y = activate(acc_at(acc, 1, c, q) + bias, use_tanh);
-            lo.z = activate(acc_at(acc, 2, c, q) + bias, use_tanh); lo.w = activate(acc_at(acc, 3, c, q) + bias, use_tanh);
-            hi.x = activate(acc_at(acc, 4, c, q) + bias, use_tanh); hi.y = activate(acc_at(acc, 5, c, q) + bias, use_tanh);
-            hi.z = activate(acc_at(acc, 6, c, q) + bias, use_tanh); hi.w = activate(acc_at(acc, 7, c, q) + bias, use_tanh);
-            *reinterpret_cast<float4*>(&sm.h1T[j * H1_LD + ty * 8]) = lo;
-            *reinterpret_cast<float4*>(&sm.h1T[j * H1_LD + ty * 8 + 4]) = hi;
+#pragma unroll
+            for (int i4 = 0; i4 < RT / 4; ++i4) {
+                float4 o;
+                o.x = activate(acc_at(acc, i4 * 4 + 0, c, q) + bias, use_tanh); o.y = activate(acc_at(acc, i4 * 4 + 1, c, q) + bias, use_tanh);
+                o.z = activate(acc_at(acc, i4 * 4 + 2, c, q) + bias, use_tanh); o.w = activate(acc_at(acc, i4 * 4 + 3, c, q) + bias, use_tanh);
+                *reinterpret_cast<float4*>(&sm.h1T[j * H1_LD + ty * RT + i4 * 4]) = o;
+            }
         }
     __syncthreads();      // h1T complete; W1^T region free for the W2^T stages
 
@@ -200,7 +208,7 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
 #pragma unroll 1
@@ -216,9 +224,9 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
     }
 
     // ---------------- layer 3 (heads): partial dot products over this thread's 16 hidden units
-    float part[8][3];
+    float part[RT][3];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { part[i][0] = 0.0f; part[i][1] = 0.0f; part[i][2] = 0.0f; }
+    for (int i = 0; i < RT; ++i) { part[i][0] = 0.0f; part[i][1] = 0.0f; part[i][2] = 0.0f; }
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -229,7 +237,7 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
 #pragma unroll
             for (int a = 0; a < 3; ++a) w[a] = (a < heads) ? sm.w3[a * HID + j] : 0.0f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < RT; ++i) {
                 const float h = activate(acc_at(acc, i, c, q) + bias, use_tanh);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) if (a < heads) part[i][a] = fmaf(h, w[a], part[i][a]);
@@ -238,14 +246,14 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
 #pragma unroll
     for (int off = 1; off < 16; off <<= 1)
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < RT; ++i)
 #pragma unroll
             for (int a = 0; a < 3; ++a) if (a < heads) part[i][a] += __shfl_xor_sync(0xffffffffu, part[i][a], off);
     if (tx == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < RT; ++i)
 #pragma unroll
-            for (int a = 0; a < 3; ++a) if (a < heads) sm.pre[(ty * 8 + i) * ACTP + a] = part[i][a];
+            for (int a = 0; a < 3; ++a) if (a < heads) sm.pre[(ty * RT + i) * ACTP + a] = part[i][a];
     }
     __syncthreads();
 
