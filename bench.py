@@ -347,8 +347,9 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": n * world * ke / float(dt.item()), "unit": "env-steps/s",
                "h2d_bytes_per_step": env.h2d_bytes_per_step, "d2h_bytes_per_step": env.d2h_bytes_per_step,
-               "api": "EnvBatch.step_host(pa, ea) -> (obs, reward, done) = one sat_env_step_host call: pinned host arrays in/out, "
-                      "2 env ranges pipelined over 2 CUDA streams (H2D, kernels and D2H of different ranges overlap); wall clock",
+               "api": "EnvBatch.step_host(pa, ea) -> (obs, reward, done) = one sat_env_step_host call on pinned host arrays: the "
+                      "kernels read the actions from and write obs/reward/done to host memory directly (UVA zero-copy over PCIe, "
+                      "overlapped with compute), then the stream is synchronised; wall clock",
                "steps": ke}
     # ---------------- PPO samples/sec (BASELINE config 5 shape, per-GPU share): rollout + GAE + K-epoch update
     ppo = None

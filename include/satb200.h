@@ -129,7 +129,9 @@ int sat_danger_zone_count(const double* rv, const double* dv, int64_t n, double 
 /* host-buffer form of step(): actions from (pinned) host memory, obs_f32/reward/done to host memory, synchronised
  * before returning. d_io is a caller-provided device staging buffer of sat_env_step_host_bytes(n) bytes.
  * With aux_stream != NULL and chunks > 1 (<= 16) the batch is cut into env ranges that alternate between `stream` and
- * `aux_stream`, so the H2D copies, the kernels and the D2H copies of different ranges overlap. */
+ * `aux_stream`, so the H2D copies, the kernels and the D2H copies of different ranges overlap.
+ * chunks == 0 selects the zero-copy form: when all five host buffers are pinned (UVA-mapped) they are passed to the
+ * kernels directly and results stream to host memory while the kernels run (falls back to staged copies otherwise). */
 int64_t sat_env_step_host_bytes(int64_t n);
 int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* ea_host,
                       float* obs_host, double* reward_host, uint8_t* done_host, void* d_io,
