@@ -349,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
                "h2d_bytes_per_step": env.h2d_bytes_per_step, "d2h_bytes_per_step": env.d2h_bytes_per_step,
                "api": "EnvBatch.step_host(pa, ea) -> (obs, reward, done) = one sat_env_step_host call on pinned host arrays: the "
                       "kernels read the actions from and write obs/reward/done to host memory directly (UVA zero-copy over PCIe, "
-                      "overlapped with compute), then the stream is synchronised; wall clock",
+                      "overlapped with compute; two env ranges on two streams), then the streams are synchronised; wall clock",
                "steps": ke}
     # ---------------- PPO samples/sec (BASELINE config 5 shape, per-GPU share): rollout + GAE + K-epoch update
     ppo = None

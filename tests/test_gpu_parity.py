@@ -221,7 +221,7 @@ def test_env_step_host_buffers(golden, oracle, eng):
     for t in range(10):
         pa = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
         ea = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
-        obs, r, d = env.step_host(pa, ea, chunks=(1, 2, 4, 0)[t % 4])                    # single-range / pipelined / zero-copy forms
+        obs, r, d = env.step_host(pa, ea, chunks=(1, 2, 4, 0, -2)[t % 5])                # single-range / pipelined / zero-copy forms
         o_obs, o_r, o_d = orc.step(pa.astype(np.float64), ea.astype(np.float64))
         assert np.array_equal(d, o_d) and np.array_equal(r, o_r) and np.array_equal(obs, o_obs.astype(np.float32))
 

@@ -8,7 +8,7 @@ env = eng.EnvBatch(n, mode="rk4", substeps=100, h=1.0, d_capture=20000.0, max_ep
 pa, ea, obs, rew, done = env.host_buffers()
 rng = np.random.default_rng(0)
 pa[...] = rng.uniform(-2, 2, (n, 3)); ea[...] = rng.uniform(-2, 2, (n, 3))
-for ch in (0, 1, 2, 4):
+for ch in (0, -2, -3, -4, 2):
     for _ in range(3): env.step_host(pa, ea, chunks=ch)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(20): env.step_host(pa, ea, chunks=ch)
