@@ -123,6 +123,15 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def guard_device(device) -> None:
+    """kernels launch on the CURRENT device: refuse to run when it is not the one that owns the buffers"""
+    import torch
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if torch.cuda.current_device() != idx:
+        raise SatError(f"current CUDA device is {torch.cuda.current_device()} but the buffers live on cuda:{idx}; "
+                       "wrap the call in `with torch.cuda.device(...)` or call torch.cuda.set_device first")
+
+
 def ptr(t) -> int:
     """device pointer of a CUDA tensor (None -> NULL)."""
     if t is None:

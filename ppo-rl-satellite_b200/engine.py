@@ -184,6 +184,7 @@ class EnvBatch:
 
     def init(self):
         """constructor state + reset() (environment.py:26-62, 66-79)."""
+        L.guard_device(self.device)
         L.check(self.lib.sat_env_init(C.byref(self.st), self._fuel0[0], self._fuel0[1], C.byref(self.params),
                                       L.stream_ptr()), "sat_env_init")
 
@@ -208,6 +209,7 @@ class EnvBatch:
         """One step() of every env. pa/ea: CUDA [n,3] float32 or float64. Outputs are written into the
         given tensors (allocated by the caller to keep the hot loop allocation-free)."""
         torch = self.torch
+        L.guard_device(self.device)
         if pa.dtype != ea.dtype or pa.dtype not in (torch.float32, torch.float64):
             raise L.SatError("actions must both be float32 or both float64")
         self.params.action_dtype = L.ACT_F32 if pa.dtype == torch.float32 else L.ACT_F64
@@ -396,6 +398,7 @@ class GaussianActorKernel:
                obs_out=None):
         """obs: CUDA fp32 [n,18]; or env=EnvBatch to read (and optionally normalise) the state directly."""
         torch = self.torch
+        L.guard_device(self.device)
         if self.w is None:
             raise L.SatError("weights not loaded")
         n = obs.shape[0] if obs is not None else env.n

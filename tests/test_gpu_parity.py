@@ -561,3 +561,33 @@ def test_full_size_env_batch_subset_vs_oracle(golden, oracle, eng):
         assert np.array_equal(obs.cpu().numpy()[sub][ok], o_obs[ok])
     assert flipped.sum() <= 3
     assert int(env.err.sum()) == 0 and int(env.done.sum()) >= 0
+
+
+def test_empty_and_invalid_sizes_return_error_codes(eng):
+    """empty inputs are argument errors (SAT_ERR_SIZE = -2), never a launch"""
+    from ppo_rl_satellite_b200 import _lib as L
+    import ctypes as C
+    lib = L.load()
+    x = torch.zeros(64, dtype=torch.float64, device="cuda")
+    i32 = torch.zeros(64, dtype=torch.int32, device="cuda")
+    f32 = torch.zeros(64, dtype=torch.float32, device="cuda")
+    u8 = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    st = L.SatEnvState(x.data_ptr(), i32.data_ptr(), 0, 0)
+    p = L.default_params()
+    assert lib.sat_env_init(C.byref(st), 320.0, 320.0, C.byref(p), None) == -2
+    assert lib.sat_env_step(C.byref(st), f32.data_ptr(), f32.data_ptr(), None, None, None, None, x.data_ptr(), u8.data_ptr(),
+                            None, None, None, None, C.byref(p), None) == -2
+    st_odd = L.SatEnvState(x.data_ptr(), i32.data_ptr(), 3, 3)            # ld must be even
+    assert lib.sat_env_observe(C.byref(st_odd), f32.data_ptr(), None, None) == -2
+    assert lib.sat_gae(f32.data_ptr(), f32.data_ptr(), u8.data_ptr(), None, 0, 4, 0.99, 0.95, f32.data_ptr(), f32.data_ptr(), None) == -2
+    assert lib.sat_gae_flat(f32.data_ptr(), f32.data_ptr(), f32.data_ptr(), f32.data_ptr(), f32.data_ptr(), 0, 0.99, 0.95,
+                            f32.data_ptr(), f32.data_ptr(), None) == -2
+    assert lib.sat_norm_update(x.data_ptr(), x.data_ptr(), 0, 18, 1, None, None, x.data_ptr(), None) == -2
+    assert lib.sat_norm_update(x.data_ptr(), x.data_ptr(), 4, 33, 1, None, None, x.data_ptr(), None) == -2   # dim > 32
+    assert lib.sat_danger_zone_count(x.data_ptr(), x.data_ptr(), 0, 3.986e14, i32.data_ptr(), None, None) == -2
+    assert lib.sat_cw_ode_rk45(x.data_ptr(), 4, 4, -1.0, 1.0, 1.0, 1.0, 1e-3, 1e-6, None, None) == -2
+    w = L.SatActorWeights()
+    assert lib.sat_actor_sample(C.byref(w), f32.data_ptr(), None, None, 4, 0, 0, 0, None, f32.data_ptr(), f32.data_ptr(),
+                                None, None, None, None) == -1            # weights not packed
+    with pytest.raises(L.SatError):
+        eng.EnvBatch(0)
