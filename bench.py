@@ -316,6 +316,42 @@ def run_ours(args, rank, world, local_rank):
         full_step(cnt[0]); cnt[0] += 1
     t_full, t_full_min = time_kernel(_full)
     t_act, t_act_min = time_kernel(lambda: pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=0, act=buf_act[k], logp=buf_logp[k]))
+    # the same full step as 4 independent env shards ("virtual ranks": own running statistics, own stream) so that the
+    # FP32 actor kernels of one shard overlap the FP64 env kernels of another
+    def sharded_full_step_ms(parts_n=4, K=10):
+        parts, streams = [], [torch.cuda.Stream(device=dev) for _ in range(parts_n)]
+        m = n // parts_n
+        for r_ in range(parts_n):
+            e_ = eng.EnvBatch(m, mode="rk4", substeps=S, h=1.0, d_capture=20000.0, max_episode_steps=1000, device=dev)
+            rr_ = np.random.default_rng(77 + r_)
+            e_.set_state(np.array([200000.0, 0, 0]) + rr_.normal(0, 3e4, (m, 3)), rr_.normal(0, 3.0, (m, 3)),
+                         np.array([18000.0, 0, 0]) + rr_.normal(0, 3e4, (m, 3)), rr_.normal(0, 3.0, (m, 3)))
+            st_, rs_ = eng.RunningStats(18, dev), eng.RunningStats(1, dev)
+            st_.update_normalize(e_.observe())
+            parts.append((e_, st_, rs_, torch.zeros(1, dtype=torch.float64, device=dev)))
+
+        def run(k0):
+            cur = torch.cuda.current_stream(dev)
+            for s_ in streams:
+                s_.wait_stream(cur)
+            for t_ in range(K):
+                for r_, (e_, st_, rs_, sd_) in enumerate(parts):
+                    lo_ = r_ * m
+                    with torch.cuda.stream(streams[r_]):
+                        pursuer.sample(env=e_, obs_stats=st_, seed=11, step=k0 + t_, row_offset=row_offset + lo_,
+                                       act=buf_act[0, lo_:lo_ + m], logp=buf_logp[0, lo_:lo_ + m], obs_out=buf_obs[0, lo_:lo_ + m])
+                        evader.sample(env=e_, obs_stats=st_, seed=12, step=k0 + t_, row_offset=row_offset + lo_,
+                                      act=buf_eact[0, lo_:lo_ + m], logp=buf_elogp[0, lo_:lo_ + m])
+                        e_.step(buf_act[0, lo_:lo_ + m], buf_eact[0, lo_:lo_ + m], reward=buf_rew[0, lo_:lo_ + m],
+                                done=buf_done[0, lo_:lo_ + m], obs_stats=st_, ret_stats=rs_, ret_std_out=sd_)
+            for s_ in streams:
+                cur.wait_stream(s_)
+        run(0)
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record(); run(K); b_.record(); b_.synchronize()
+        return a_.elapsed_time(b_) / K
+    t_full4 = sharded_full_step_ms() if n % 256 == 0 else None
     nk1 = 1 << 20
     xk1, _ = eng.alloc_soa(6, nk1, torch.float64, dev)
     ang = torch.rand(nk1, device=dev, dtype=torch.float64) * 6.283185307179586
@@ -406,7 +442,11 @@ def run_ours(args, rank, world, local_rank):
         "full_step_with_actor_sampling": {"ms_per_step": t_full, "env_steps_per_sec": n * world / (t_full * 1e-3) if world == 1 else None,
                                           "per_gpu_env_steps_per_sec": n / (t_full * 1e-3),
                                           "what": "pursuer + evader fused Gaussian actor kernels (obs rebuilt + normalised from the fp64 state, "
-                                                  "Philox sampling) + the env step above; 4 launches"},
+                                                  "Philox sampling) + the env step above; 4 launches",
+                                          "as_4_independent_shards_on_4_streams": None if t_full4 is None else {
+                                              "ms_per_step": t_full4, "per_gpu_env_steps_per_sec": n / (t_full4 * 1e-3),
+                                              "what": "the same work as 4 env shards with per-shard running statistics on 4 streams: the FP32 "
+                                                      "actor kernels of one shard overlap the FP64 env kernels of another"}},
         "ppo": ppo,
         "cpu_baseline": cpu,
         "clocks": clocks,
