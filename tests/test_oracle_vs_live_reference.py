@@ -1,0 +1,44 @@
+"""Live cross-check of the oracle against the reference itself (only where /root/reference is mounted: the build
+container). The committed fixtures pin the same thing for machines without the reference tree."""
+import numpy as np
+import pytest
+
+import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+
+
+def test_env_oracle_equals_live_reference_randomised(oracle):
+    M = oracle.cw_matrix(100.0)
+    rng = np.random.default_rng(2024)
+    total = 0
+    for trial in range(4):
+        flag, dcap, ms = trial % 2, [20000, 181000, 150000, 100000][trial], [64, 200, 1000, 30][trial]
+        env = refshim.make_env(dcap, ms)
+        oenv = oracle.Env(d_capture=float(dcap), max_episode_steps=ms, M=M)
+        assert np.array_equal(np.asarray(env.reset(flag), float), oenv.reset(flag))
+        cnt, scale = 0, [2.0, 0.5, 3.0, 2.0][trial]
+        for t in range(700):
+            cnt += 1
+            pa = rng.uniform(-scale, scale, 3).astype(np.float32).astype(np.float64)
+            ea = rng.uniform(-scale, scale, 3).astype(np.float32).astype(np.float64)
+            if rng.random() < 0.05:
+                pa[rng.integers(0, 3)] = 0.0
+            s_, r, d = refshim.quiet_step(env, pa, ea, cnt)
+            so_, ro, do = oenv.step(pa, ea, cnt)
+            assert np.array_equal(np.asarray(s_, float), so_) and float(r) == ro and bool(d) == do
+            assert env.dangerous_zone == oenv.e.dangerous_zone and float(env.fuel_c) == oenv.e.fuel_c
+            total += 1
+            if d:
+                env.reset(flag); oenv.reset(flag); cnt = 0
+    assert total == 2800
+
+
+def test_rk4_oracle_equals_live_script_functions(oracle):
+    ns = refshim.load_rk4_script(None)
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        rv = np.concatenate([rng.normal(0, 1, 3) * 4000 + [7000, 0, 0], rng.normal(0, 1, 3) + [0, 7.5, 0]])
+        ref = ns["RungeKutta"](0, rv.copy(), 1.0)
+        got = oracle.rk4_propagate(rv.reshape(6, 1), 1.0, 1)[:, 0]
+        np.testing.assert_allclose(got, ref, rtol=3e-16, atol=0)
