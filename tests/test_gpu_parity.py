@@ -591,3 +591,26 @@ def test_empty_and_invalid_sizes_return_error_codes(eng):
                                 None, None, None, None) == -1            # weights not packed
     with pytest.raises(L.SatError):
         eng.EnvBatch(0)
+
+
+def test_actor_relu_and_max_action_variants_vs_torch(eng):
+    """args.use_tanh = 0 (ReLU hidden activations, ppo_continuous.py:74) and a non-default max_action, against torch fp32"""
+    torch.manual_seed(3)
+    W = {"fc1.weight": torch.randn(256, 18) * 0.3, "fc1.bias": torch.randn(256) * 0.1, "fc2.weight": torch.randn(256, 256) * 0.08,
+         "fc2.bias": torch.randn(256) * 0.1, "mean_layer.weight": torch.randn(3, 256) * 0.05, "mean_layer.bias": torch.randn(3) * 0.1,
+         "log_std": torch.tensor([[-0.5, 0.0, 0.3]])}
+    x = torch.randn(777, 18)
+    eps = torch.randn(777, 3)
+    for use_tanh, max_action in ((False, 1.6), (True, 0.4)):
+        act_fn = torch.tanh if use_tanh else torch.relu
+        h = act_fn(act_fn(x @ W["fc1.weight"].T + W["fc1.bias"]) @ W["fc2.weight"].T + W["fc2.bias"])
+        mean_ref = max_action * torch.tanh(h @ W["mean_layer.weight"].T + W["mean_layer.bias"])
+        std = torch.exp(W["log_std"])
+        a_ref = torch.clamp(mean_ref + std * eps, -max_action, max_action)
+        lp_ref = torch.distributions.Normal(mean_ref, std.expand_as(mean_ref)).log_prob(a_ref)
+        k = eng.GaussianActorKernel(max_action=max_action, use_tanh=use_tanh).load_state_dict(W)
+        mean = torch.empty(777, 3, device="cuda")
+        a, lp = k.sample(obs=x.cuda(), eps_in=eps.cuda(), mean_out=mean)
+        torch.testing.assert_close(mean.cpu(), mean_ref, rtol=0, atol=3e-5)
+        torch.testing.assert_close(a.cpu(), a_ref, rtol=0, atol=3e-5)
+        torch.testing.assert_close(lp.cpu(), lp_ref, rtol=1e-4, atol=2e-4)
