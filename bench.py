@@ -19,7 +19,6 @@ One JSON line on stdout (rank 0). See DESIGN.md "Measurement" for every field.
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
 import subprocess

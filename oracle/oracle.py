@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY. Allowed importers: tests/, __graft_entry__.smoke(), and bench.py's
 cpu_baseline / --impl reference legs. The product package (ppo-rl-satellite_b200/) must never
-import this module; tests/test_no_oracle_in_product.py enforces that.
+import this module; tests/test_cabi_symbols.py::test_product_never_imports_the_oracle enforces that.
 """
 from __future__ import annotations
 

@@ -9,6 +9,7 @@ unchanged (ppo_continuous.py:61-134, 252-258):
 Only the Gaussian policy is on the CUDA path (policy_dist == "Beta" is out of the north star's scope).
 """
 import os
+import zlib
 
 import numpy as np
 import torch
@@ -123,7 +124,8 @@ class PPO_continuous:
         self._use_tanh = bool(args.use_tanh)
         self.actor_kernel = _eng.GaussianActorKernel(max_action=self.max_action, use_tanh=self._use_tanh, device=self.device)
         self.critic_kernel = _eng.GaussianActorKernel(use_tanh=self._use_tanh, device=self.device, critic=True)
-        self.seed, self._step = int(seed) + (hash(str(agent_idx)) & 0xffff), 0
+        # per-agent Philox key offset; crc32 (not hash()) so that it is the same in every process and run
+        self.seed, self._step = int(seed) + (zlib.crc32(str(agent_idx).encode()) & 0xffff), 0
         self._dirty = True
 
     # ---- kernel-side weight image follows the torch parameters
