@@ -221,6 +221,14 @@ int sat_orbital_elements(const double* rv, int64_t n, double miu, double* elemen
 /* calculate_state_information(data, miu) (satellite_function.py:257-315), six-element form: -> rv [n][6]. */
 int sat_state_from_elements(const double* elements, int64_t n, double miu, double* rv_out, void* stream);
 
+/* Reachable-domain sweep. Replaces Reachable_Domain() of single_pluse_model/RD_single_pulse.py:40-148
+ * (N1 = 1) for n pursuer states given as elements [n][6] = (a, e, i, omega, Omega, f) and delta_max [n]: for each of the
+ * (N2+1)*(N3+1) directions (i major, j minor - the reference's loop order) the reachability test and the two fsolve
+ * extremes. rf_max / rf_min [n][(N2+1)*(N3+1)][3] = max / min |rf| times the direction vector, valid [n][...] = 1 for the
+ * directions the reference appends to its point clouds. The ellipse fit that follows upstream is out of scope. n <= 65535. */
+int sat_reachable_domain(const double* elements, const double* delta_max, int64_t n, int N2, int N3, double u,
+                         double* rf_max, double* rf_min, uint8_t* valid, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): dependent-free DFMA / FFMA chains to measure the FP64 / FP32
  * vector peaks on the device the bench runs on (MEASURED_PEAKS.json has no such entries).

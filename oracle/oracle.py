@@ -65,6 +65,7 @@ def lib():
         L.orc_danger_zone_debug.restype = i32
         L.orc_cw_ode_rk45.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int)]
         L.orc_cw_ode_rk45.restype = i32
+        L.orc_reachable_domain.argtypes = [dp, C.c_double, i32, i32, C.c_double, dp, dp, C.POINTER(C.c_uint8)]
         L.orc_env_init.argtypes = [C.POINTER(OrcEnv), C.c_double, C.c_double, C.c_double, C.c_double, i32]
         L.orc_env_reset.argtypes = [C.POINTER(OrcEnv), i32, dp]
         L.orc_env_step.argtypes = [C.POINTER(OrcEnv), dp, dp, dp, i32, dp, dp]
@@ -179,6 +180,18 @@ def danger_zone_debug(Rc, Vc, Rt, Vt, dv, u=MU_M):
     dbg = np.zeros(16)
     c = lib().orc_danger_zone_debug(_dp(Rc), _dp(Vc), _dp(Rt), _dp(Vt), float(dv), float(u), _dp(dbg))
     return c, dbg.reshape(2, 8)
+
+
+def reachable_domain(el, delta_max, N2=200, N3=200, u=MU_M):
+    """RD_single_pulse.Reachable_Domain sweep -> (RF_max [K,3], RF_min [K,3]) in the reference's append order, plus the mask"""
+    el = _f64(el)
+    m = (N2 + 1) * (N3 + 1)
+    hi, lo = np.zeros((m, 3)), np.zeros((m, 3))
+    valid = np.zeros(m, dtype=np.uint8)
+    lib().orc_reachable_domain(_dp(el), float(delta_max), int(N2), int(N3), float(u), _dp(hi), _dp(lo),
+                               valid.ctypes.data_as(C.POINTER(C.c_uint8)))
+    v = valid.astype(bool)
+    return hi[v], lo[v], v
 
 
 # ------------------------------------------------------------------ env

@@ -815,3 +815,53 @@ int orc_cw_ode_rk45(double y[6], double t_bound, double w2, double w3, double wz
     if (nsteps_out) *nsteps_out = nsteps;
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Reachable-domain sweep, single_pluse_model/RD_single_pulse.py:40-148 (Reachable_Domain, N1 = 1): for every direction
+ * (gama_i, alpha_j), i <= N2, j <= N3, the reachability test and the two fsolve extremes. Output order = the reference's
+ * append order (i major, j minor); valid[i*(N3+1)+j] marks the directions the reference appends.
+ * ------------------------------------------------------------------------------------------ */
+void orc_reachable_domain(const double el[6], double delta_max, int N2, int N3, double u,
+                          double* rf_max_xyz, double* rf_min_xyz, uint8_t* valid) {
+    double a = el[0], e0 = el[1], f = el[5];
+    double r0 = a * (1 - SQ(e0)) / (1 + e0 * cos(f));                          /* :47 */
+    double p0 = a * (1 - SQ(e0));                                              /* :48 */
+    double Delta_V = -delta_max + 2 * delta_max * 1 / 1;                       /* :65, N1 = 1 */
+    int i, j;
+    for (i = 0; i <= N2; ++i) {
+        double gama = 2 * ORC_PI * i / N2;                                     /* :67 */
+        for (j = 0; j <= N3; ++j) {
+            double alpha = -ORC_PI / 2 + ORC_PI * j / N3;                      /* :69 */
+            double P[3] = {sin(gama) * cos(alpha), cos(gama) * cos(alpha), sin(alpha)};   /* :72 */
+            double temp1 = SQ(sin(gama - f)) / (u * SQ(1 + e0 * cos(f)) / (p0 * SQ(Delta_V)) - 1);   /* :80 */
+            double t2 = SQ(tan(alpha));
+            int64_t o = (int64_t)i * (N3 + 1) + j;
+            int k;
+            valid[o] = 0;
+            for (k = 0; k < 3; ++k) { rf_max_xyz[o * 3 + k] = 0; rf_min_xyz[o * 3 + k] = 0; }
+            if (0 <= t2 && t2 <= temp1) {                                      /* :82 */
+                double beta = atan(tan(alpha) / sin(gama - f));                /* :83 */
+                double Delta_Vm = sqrt(SQ(Delta_V) - u * SQ(1 + e0 * cos(f)) * SQ(sin(beta)) / p0);   /* :85 */
+                double df = gama - f, theta = 0, rf[2], lo, hi;
+                int g, have = 0;
+                if ((-2 * ORC_PI <= df && df < -ORC_PI) || (0 <= df && df < ORC_PI)) { theta = acos(cos(df) * cos(alpha)); have = 1; }   /* :88-89 */
+                else if ((-ORC_PI <= df && df < 0) || (ORC_PI <= df && df < 2 * ORC_PI)) { theta = 2 * ORC_PI - acos(cos(df) * cos(alpha)); have = 1; }
+                (void)have;   /* outside both ranges python keeps theta from the previous direction; gama - f stays inside for f in [0, 2pi) */
+                for (g = 0; g < 2; ++g) {
+                    double ag = g == 0 ? ORC_PI / 2 : -ORC_PI / 2;             /* :94 / :109 */
+                    double v_1x = sqrt(u / p0) * e0 * sin(f) + Delta_Vm * cos(ag);
+                    double v_1y = sqrt(u / p0) * (1 + e0 * cos(f)) * cos(beta) + Delta_Vm * sin(ag);
+                    double h = r0 * v_1y;
+                    double al = orc_numerical_iteration(u, Delta_Vm, theta, v_1x, v_1y, h, ag);
+                    double vx = sqrt(u / p0) * e0 * sin(f) + Delta_Vm * cos(al);
+                    double vy = sqrt(u / p0) * (1 + e0 * cos(f)) * cos(beta) + Delta_Vm * sin(al);
+                    double hm = r0 * vy;
+                    rf[g] = SQ(hm) / (u * (1 - cos(theta)) + hm * vy * cos(theta) - hm * vx * sin(theta));   /* :107 / :121 */
+                }
+                hi = fmax(fabs(rf[0]), fabs(rf[1])); lo = fmin(fabs(rf[0]), fabs(rf[1]));   /* :123-124 */
+                for (k = 0; k < 3; ++k) { rf_max_xyz[o * 3 + k] = hi * P[k]; rf_min_xyz[o * 3 + k] = lo * P[k]; }
+                valid[o] = 1;
+            }
+        }
+    }
+}

@@ -98,6 +98,10 @@ void orc_env_step_rk4_batch(orc_env* envs, int32_t* counts, int64_t n, double h,
  * y in/out, returns 0 or -1 (step too small) ---- */
 int orc_cw_ode_rk45(double y[6], double t_bound, double w2, double w3, double wz, int* nsteps_out);
 
+/* ---- reachable-domain sweep (single_pluse_model/RD_single_pulse.py:40-148, N1 = 1); outputs [(N2+1)*(N3+1)][3] and a mask ---- */
+void orc_reachable_domain(const double el[6], double delta_max, int N2, int N3, double u,
+                          double* rf_max_xyz, double* rf_min_xyz, uint8_t* valid);
+
 /* ---- normalisation (normalization.py:7-63) ---- */
 typedef struct { int64_t n; int dim; double* mean; double* S; double* std; } orc_rms;
 void orc_rms_update(orc_rms* r, const double* x);                       /* :19-29 incl. n==1 rule */

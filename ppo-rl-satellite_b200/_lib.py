@@ -53,6 +53,7 @@ SIGNATURES = {
     "sat_state_eq": (C.c_int, [_P, _P, _I64, _I64, _D, _D, _D, _P]),
     "sat_cw_propagate": (C.c_int, [_P, _I64, _I64, C.POINTER(C.c_double), _P]),
     "sat_cw_ode_rk45": (C.c_int, [_P, _I64, _I64, _D, _D, _D, _D, _D, _D, _P, _P]),
+    "sat_reachable_domain": (C.c_int, [_P, _P, _I64, _I32, _I32, _D, _P, _P, _P, _P]),
     "sat_orbital_elements": (C.c_int, [_P, _I64, _D, _P, _P, _P]),
     "sat_state_from_elements": (C.c_int, [_P, _I64, _D, _P, _P]),
     "sat_workspace_bytes": (_I64, [_I64]),

@@ -27,6 +27,7 @@ UNITS = {
     "env_step.cu": ["-fmad=false"],
     "gae.cu": ["-fmad=false"],
     "cw_ode.cu": ["-fmad=false"],
+    "reach.cu": ["-fmad=false"],
     "actor.cu": [],
     "capi.cu": [],
 }

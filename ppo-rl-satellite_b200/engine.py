@@ -352,6 +352,21 @@ def danger_zone_count(rv, dv, u=MU_M, debug=False):
     return (out, dbg) if debug else out
 
 
+def reachable_domain(elements, delta_max, N2=200, N3=200, u=MU_M):
+    """Batched RD_single_pulse.Reachable_Domain sweep. elements: CUDA fp64 [n,6] (a,e,i,omega,Omega,f); delta_max [n].
+    -> rf_max [n,D,3], rf_min [n,D,3], valid [n,D] (uint8), D = (N2+1)*(N3+1) directions in the reference's loop order."""
+    torch = L.require_cuda()
+    elements, delta_max = elements.contiguous(), delta_max.contiguous()
+    n = elements.shape[0]
+    D = (N2 + 1) * (N3 + 1)
+    hi = torch.empty((n, D, 3), dtype=torch.float64, device=elements.device)
+    lo = torch.empty((n, D, 3), dtype=torch.float64, device=elements.device)
+    valid = torch.empty((n, D), dtype=torch.uint8, device=elements.device)
+    L.check(L.load().sat_reachable_domain(L.ptr(elements), L.ptr(delta_max), n, int(N2), int(N3), float(u), L.ptr(hi),
+                                          L.ptr(lo), L.ptr(valid), L.stream_ptr()), "sat_reachable_domain")
+    return hi, lo, valid
+
+
 # --------------------------------------------------------------------------------------------- K3
 class GaussianActorKernel:
     """Fused Actor_Gaussian forward + sampling (ppo_continuous.py:83-95, 176-189) for batches."""

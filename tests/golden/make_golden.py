@@ -319,8 +319,26 @@ def gen_ode():
     save("ode_golden.npz", state_c=sc, state_t=st, t=ts, out_c=np.array(oc), out_t=np.array(ot))
 
 
+def gen_reach():
+    """RD_single_pulse.Reachable_Domain point clouds (captured before the ellipse fit), reduced sweep N2 = N3 = 40"""
+    import importlib
+    refshim.load()
+    sys.path.insert(0, REF)
+    RD = importlib.import_module("single_pluse_model.RD_single_pulse")
+    cap = {}
+    RD.cf.Curve_fitting = lambda a, b: (cap.__setitem__("a", a), cap.__setitem__("b", b), [0] * 10)[2]
+    RD.params["N2"], RD.params["N3"] = 40, 40
+    g = np.load(os.path.join(HERE, "elements_golden.npz"))
+    idx = np.array([0, 100, 300, 500, 700, 840])
+    out = {"idx": idx, "elements": g["elements_live"][idx], "delta_max": g["fuel"][idx], "N": np.int32(40)}
+    for n, k in enumerate(idx):
+        RD.Incoming_parameters(list(g["elements_live"][k]), float(g["fuel"][k]))
+        out[f"rf_max_{n}"], out[f"rf_min_{n}"] = np.asarray(cap["a"]), np.asarray(cap["b"])
+    save("reach_golden.npz", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rk4", "elements", "env", "danger", "ppo", "norm", "ode"]
+    which = sys.argv[1:] or ["rk4", "elements", "env", "danger", "ppo", "norm", "ode", "reach"]
     if "rk4" in which: gen_rk4()
     if "elements" in which: gen_elements()
     if "env" in which: gen_env()
@@ -328,3 +346,4 @@ if __name__ == "__main__":
     if "ppo" in which: gen_ppo()
     if "norm" in which: gen_norm()
     if "ode" in which: gen_ode()
+    if "reach" in which: gen_reach()

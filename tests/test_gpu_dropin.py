@@ -260,3 +260,17 @@ def test_self_play_alternates_learners(mods, tmp_path):
     assert env.params.flag == 1 and np.isfinite(log[0]["mean_reward"])
     assert any(not torch.equal(a, b.detach()) for a, b in zip(e0, evader.actor.parameters()))
     assert all(torch.equal(a, b.detach()) for a, b in zip(p1, pursuer.actor.parameters()))
+
+
+def test_rd_single_pulse_facade_matches_reference_clouds(golden):
+    """single_pluse_model/RD_single_pulse.py:22-148 up to the clouds handed to the ellipse fit"""
+    from ppo_rl_satellite_b200.dropin import rd_single_pulse as RD
+    g = golden("reach_golden.npz")
+    RD.params["N2"] = RD.params["N3"] = int(g["N"])
+    try:
+        for n in (0, 1, 5):
+            hi, lo = RD.Incoming_parameters(list(g["elements"][n]), float(g["delta_max"][n]))
+            np.testing.assert_allclose(hi, g[f"rf_max_{n}"], rtol=1e-9, atol=1e-3)
+            np.testing.assert_allclose(lo, g[f"rf_min_{n}"], rtol=1e-9, atol=1e-3)
+    finally:
+        RD.params["N2"] = RD.params["N3"] = 200

@@ -614,3 +614,23 @@ def test_actor_relu_and_max_action_variants_vs_torch(eng):
         torch.testing.assert_close(mean.cpu(), mean_ref, rtol=0, atol=3e-5)
         torch.testing.assert_close(a.cpu(), a_ref, rtol=0, atol=3e-5)
         torch.testing.assert_close(lp.cpu(), lp_ref, rtol=1e-4, atol=2e-4)
+
+
+# ============================================================================ reachable-domain sweep (s8 f.3)
+def test_reachable_domain_sweep_vs_reference_and_oracle(golden, oracle, eng):
+    g = golden("reach_golden.npz")
+    N = int(g["N"])
+    hi, lo, valid = eng.reachable_domain(torch.from_numpy(g["elements"]).cuda(), torch.from_numpy(g["delta_max"]).cuda(), N, N)
+    hi, lo, valid = hi.cpu().numpy(), lo.cpu().numpy(), valid.cpu().numpy().astype(bool)
+    for n in range(len(g["idx"])):
+        assert valid[n].sum() == len(g[f"rf_max_{n}"])               # same directions pass the reachability test
+        np.testing.assert_allclose(hi[n][valid[n]], g[f"rf_max_{n}"], rtol=1e-9, atol=1e-3)
+        np.testing.assert_allclose(lo[n][valid[n]], g[f"rf_min_{n}"], rtol=1e-9, atol=1e-3)
+    # full 201 x 201 sweep (the reference's N2 = N3 = 200) for two states against the oracle
+    for n in (0, 3):
+        h2, l2, v2 = eng.reachable_domain(torch.from_numpy(g["elements"][n:n + 1]).cuda(), torch.from_numpy(g["delta_max"][n:n + 1]).cuda())
+        oh, ol, ov = oracle.reachable_domain(g["elements"][n], g["delta_max"][n], 200, 200)
+        v2 = v2.cpu().numpy()[0].astype(bool)
+        assert np.array_equal(v2, ov)
+        np.testing.assert_allclose(h2.cpu().numpy()[0][v2], oh, rtol=1e-9, atol=1e-3)
+        np.testing.assert_allclose(l2.cpu().numpy()[0][v2], ol, rtol=1e-9, atol=1e-3)

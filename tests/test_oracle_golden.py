@@ -177,3 +177,14 @@ def test_cw_ode_rk45_matches_reference(golden, oracle):
             y, nsteps = oracle.cw_ode_rk45(y0, g["t"][k])
             assert 2 <= nsteps <= 8
             np.testing.assert_allclose(y, ref, rtol=2e-12, atol=1e-9)
+
+
+# ------------------------------------------------------------------ reachable-domain sweep (RD_single_pulse.py:40-148)
+def test_reachable_domain_sweep_matches_reference(golden, oracle):
+    g = golden("reach_golden.npz")
+    N = int(g["N"])
+    for n in range(len(g["idx"])):
+        hi, lo, valid = oracle.reachable_domain(g["elements"][n], g["delta_max"][n], N, N)
+        assert hi.shape == g[f"rf_max_{n}"].shape and valid.sum() > 10
+        np.testing.assert_allclose(hi, g[f"rf_max_{n}"], rtol=1e-12, atol=1e-6)
+        np.testing.assert_allclose(lo, g[f"rf_min_{n}"], rtol=1e-12, atol=1e-6)
