@@ -230,6 +230,45 @@ int sat_reachable_domain(const double* elements, const double* delta_max, int64_
                          double* rf_max, double* rf_min, uint8_t* valid, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused PPO minibatch step. Replaces the body of the K-epoch loop of PPO_continuous.update
+ * (ppo_continuous.py:216-239): actor clipped-surrogate + entropy loss, critic MSE loss, their backward passes through
+ * the 18-256-256-{3,1} MLPs, clip_grad_norm_ and the Adam step (:161-163). fp32 CUDA-core FFMA2, no tensor cores.
+ *
+ * One network's parameters live in ONE flat fp32 buffer in torch parameter order (fc1.weight [256][18], fc1.bias,
+ * fc2.weight [256][256], fc2.bias, mean_layer/fc3.weight [heads][256], bias [heads], log_std [3] for the actor), so the
+ * torch modules can hold views of it and the gradient all-reduce is one NCCL call on `grads`. */
+enum { SAT_PPO_OFF_W1 = 0, SAT_PPO_OFF_B1 = 4608, SAT_PPO_OFF_W2 = 4864, SAT_PPO_OFF_B2 = 70400, SAT_PPO_OFF_W3 = 70656 };
+#define SAT_PPO_PARAM_FLOATS(heads) (70656 + 257 * (heads) + ((heads) == 3 ? 3 : 0))   /* actor 71430, critic 70913 */
+
+typedef struct SatPpoNet {
+    float* params;      /* flat parameters (SAT_PPO_OFF_*), updated in place by sat_ppo_adam; 16-byte aligned */
+    float* packed;      /* SAT_ACTOR_PACKED_FLOATS kernel image of params (what sat_actor_sample reads); rewritten by sat_ppo_adam */
+    float* grads;       /* flat gradient, same layout, SAT_PPO_PARAM_FLOATS + 1 floats: the last one is the minibatch loss */
+    float* exp_avg;     /* Adam first moment, flat */
+    float* exp_avg_sq;  /* Adam second moment, flat */
+    float* workspace;   /* sat_ppo_workspace_floats(mb) floats, may be shared by the two networks of one agent */
+    int32_t heads;      /* 3 = Actor_Gaussian, 1 = Critic */
+    int32_t use_tanh;   /* hidden activation: 1 tanh, 0 ReLU */
+    float max_action;
+    int32_t reserved;
+} SatPpoNet;
+
+int64_t sat_ppo_workspace_floats(int64_t mb);
+/* rebuild `packed` from `params` (after loading a checkpoint into the torch views) */
+int sat_ppo_pack(const SatPpoNet* net, void* stream);
+/* gradient of mean(-min(ratio*adv, clamp(ratio, 1-eps, 1+eps)*adv) - entropy_coef*entropy) over the minibatch rows
+ * index[0..mb) of s [B][18], a [B][3], old_logp [B][3], adv [B] (index == NULL: rows 0..mb) -> net->grads */
+int sat_ppo_actor_grad(const SatPpoNet* net, const float* s, const float* a, const float* old_logp, const float* adv,
+                       const int64_t* index, int64_t mb, float epsilon, float entropy_coef, void* stream);
+/* gradient of mse_loss(v_target[index], critic(s[index])) -> net->grads */
+int sat_ppo_critic_grad(const SatPpoNet* net, const float* s, const float* v_target, const int64_t* index, int64_t mb,
+                        void* stream);
+/* grads *= grad_scale (1/world after an all-reduce); clip_grad_norm_(max_grad_norm) when max_grad_norm > 0; Adam with
+ * the learning rate read from device memory (*lr) and the step counter *step (device, incremented here) */
+int sat_ppo_adam(const SatPpoNet* net, const float* lr, float beta1, float beta2, float eps, float max_grad_norm,
+                 float grad_scale, int64_t* step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): dependent-free DFMA / FFMA chains to measure the FP64 / FP32
  * vector peaks on the device the bench runs on (MEASURED_PEAKS.json has no such entries).
  * Each launches one kernel doing `iters` x 16 independent FMAs per thread; flops_out (host) receives

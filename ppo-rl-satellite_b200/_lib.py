@@ -44,6 +44,19 @@ class SatActorWeights(C.Structure):
 
 
 # name -> (restype, argtypes); kept in one table so tests can check it against include/satb200.h
+class SatPpoNet(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("packed", C.c_void_p), ("grads", C.c_void_p), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("workspace", C.c_void_p), ("heads", C.c_int32), ("use_tanh", C.c_int32),
+                ("max_action", C.c_float), ("reserved", C.c_int32)]
+
+
+PPO_OFF_W1, PPO_OFF_B1, PPO_OFF_W2, PPO_OFF_B2, PPO_OFF_W3 = 0, 4608, 4864, 70400, 70656
+
+
+def ppo_param_floats(heads: int) -> int:
+    return 70656 + 257 * heads + (3 if heads == 3 else 0)
+
+
 _P, _I64, _I32, _D, _F, _U64 = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_float, C.c_uint64
 SIGNATURES = {
     "sat_abi_version": (C.c_int, []),
@@ -53,6 +66,11 @@ SIGNATURES = {
     "sat_state_eq": (C.c_int, [_P, _P, _I64, _I64, _D, _D, _D, _P]),
     "sat_cw_propagate": (C.c_int, [_P, _I64, _I64, C.POINTER(C.c_double), _P]),
     "sat_cw_ode_rk45": (C.c_int, [_P, _I64, _I64, _D, _D, _D, _D, _D, _D, _P, _P]),
+    "sat_ppo_workspace_floats": (C.c_int64, [_I64]),
+    "sat_ppo_pack": (C.c_int, [_P, _P]),
+    "sat_ppo_actor_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _P]),
+    "sat_ppo_critic_grad": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
+    "sat_ppo_adam": (C.c_int, [_P, _P, _F, _F, _F, _F, _F, _P, _P]),
     "sat_reachable_domain": (C.c_int, [_P, _P, _I64, _I32, _I32, _D, _P, _P, _P, _P]),
     "sat_orbital_elements": (C.c_int, [_P, _I64, _D, _P, _P, _P]),
     "sat_state_from_elements": (C.c_int, [_P, _I64, _D, _P, _P]),

@@ -121,6 +121,7 @@ class PPO_continuous:
         self.optimizer_actor = torch.optim.Adam(self.actor.parameters(), lr=torch.tensor(float(self.lr_a), device=self.device), **eps, **cap)
         self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=torch.tensor(float(self.lr_c), device=self.device), **eps, **cap)
         self._graph = None
+        self._fused = None
         self._use_tanh = bool(args.use_tanh)
         self.actor_kernel = _eng.GaussianActorKernel(max_action=self.max_action, use_tanh=self._use_tanh, device=self.device)
         self.critic_kernel = _eng.GaussianActorKernel(use_tanh=self._use_tanh, device=self.device, critic=True)
@@ -130,9 +131,58 @@ class PPO_continuous:
 
     # ---- kernel-side weight image follows the torch parameters
     def sync_kernels(self):
-        self.actor_kernel.load_state_dict(self.actor.state_dict())
-        self.critic_kernel.load_state_dict(self.critic.state_dict())
+        if self._fused is not None and all(n.adopted() for n in self._fused["nets"]):
+            for n in self._fused["nets"]:            # device-side repack of the flat parameters
+                n.pack()
+        else:
+            self.actor_kernel.load_state_dict(self.actor.state_dict())
+            self.critic_kernel.load_state_dict(self.critic.state_dict())
         self._dirty = False
+
+    # ---- fused CUDA minibatch step (csrc/ppo_update.cu): flat parameter buffers the torch modules hold views of
+    def _fused_for(self, mb):
+        f = self._fused
+        if f is None or not all(n.adopted() for n in f["nets"]):
+            eps = 1e-5 if self.set_adam_eps else 1e-8
+            na = _eng.PpoFusedNet(self.actor, False, self._use_tanh, self.max_action, self.optimizer_actor.param_groups[0]["lr"],
+                                  packed=self.actor_kernel.packed, eps=eps)
+            nc = _eng.PpoFusedNet(self.critic, True, self._use_tanh, 0.0, self.optimizer_critic.param_groups[0]["lr"],
+                                  packed=self.critic_kernel.packed, eps=eps)
+            if f is not None:                         # parameters were moved (e.g. module.to()): keep the Adam moments
+                na.load_state_dict(f["nets"][0].state_dict()); nc.load_state_dict(f["nets"][1].state_dict())
+            f = self._fused = {"nets": (na, nc), "mb": 0, "ws": None}
+            self.actor_kernel.w, self.critic_kernel.w = na.actor_weights(), nc.actor_weights()
+            self._graph = None                        # a captured graph holds the old parameter addresses
+        if f["mb"] < mb:
+            f["ws"] = _eng.ppo_workspace(mb, self.device)
+            f["mb"] = mb
+            for n in f["nets"]:
+                n.bind(f["ws"])
+        return f
+
+    def _optimize_fused(self, s, a, a_logprob, adv, v_target, mb, group):
+        dist = torch.distributed
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        B = s.shape[0]
+        f = self._fused_for(min(mb, B))
+        na, nc = f["nets"]
+        s, a, a_logprob = s.contiguous(), a.contiguous(), a_logprob.contiguous()
+        adv, v_target = adv.reshape(-1).contiguous(), v_target.reshape(-1).contiguous()
+        clip = 0.5 if self.use_grad_clip else 0.0
+        for _ in range(self.K_epochs):
+            perm = torch.randperm(B, device=s.device)
+            for lo in range(0, B, mb):
+                m = min(mb, B - lo)
+                index = perm.data_ptr() + 8 * lo
+                na.actor_grad(s, a, a_logprob, adv, index, m, self.epsilon, self.entropy_coef)
+                if world > 1:
+                    dist.all_reduce(na.grads, group=group)
+                na.adam(clip, 1.0 / world)
+                nc.critic_grad(s, v_target, index, m)
+                if world > 1:
+                    dist.all_reduce(nc.grads, group=group)
+                nc.adam(clip, 1.0 / world)
+        self._dirty = False                           # the Adam kernel rewrites the packed weight images itself
 
     def _obs(self, s):
         a = np.asarray(s, dtype=np.float32)
@@ -231,11 +281,14 @@ class PPO_continuous:
         self._graph = {"key": key, "graph": g, "idx": idx}
         return self._graph
 
-    def optimize(self, s, a, a_logprob, adv, v_target, mini_batch_size=None, group=None, use_graph=False):
+    def optimize(self, s, a, a_logprob, adv, v_target, mini_batch_size=None, group=None, use_graph=False, fused=False):
         """K epochs of clipped-PPO minibatch steps (ppo_continuous.py:213-239) on device tensors.
-        use_graph: replay one captured CUDA graph per minibatch (static buffers, full minibatches only)."""
+        fused: the hand-written forward/backward/Adam kernels (own Adam moments, independent of the torch optimisers);
+        use_graph: replay one captured CUDA graph of the PyTorch step per minibatch (static buffers, full minibatches only)."""
         B = s.shape[0]
         mb = mini_batch_size or self.mini_batch_size
+        if fused:
+            return self._optimize_fused(s, a, a_logprob, adv, v_target, mb, group)
         tensors = (s, a, a_logprob, adv, v_target)
         graph = None
         if use_graph and B >= mb:

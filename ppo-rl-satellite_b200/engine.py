@@ -437,6 +437,103 @@ class GaussianActorKernel:
         return out
 
 
+# --------------------------------------------------------------------------------------------- fused PPO step
+class PpoFusedNet:
+    """One network of the fused PPO minibatch step (csrc/ppo_update.cu): flat parameter / gradient / Adam-moment buffers in
+    torch parameter order. `adopt(module)` re-points the torch parameters at views of the flat buffer, so the module, its
+    checkpoints and the eager PyTorch path keep seeing the weights this class updates."""
+
+    ACTOR_NAMES = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "mean_layer.weight", "mean_layer.bias", "log_std")
+    CRITIC_NAMES = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc3.weight", "fc3.bias")
+
+    def __init__(self, module, critic: bool, use_tanh: bool, max_action: float, lr, packed=None, betas=(0.9, 0.999),
+                 eps: float = 1e-8):
+        torch = L.require_cuda()
+        self.torch, self.lib, self.module, self.critic = torch, L.load(), module, critic
+        self.heads = 1 if critic else 3
+        self.n = L.ppo_param_floats(self.heads)
+        dev = next(module.parameters()).device
+        self.device = dev
+        self.params = torch.zeros(self.n + 2, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(self.n + 2, dtype=torch.float32, device=dev)        # [n] = minibatch loss
+        self.exp_avg = torch.zeros(self.n + 2, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.n + 2, dtype=torch.float32, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.packed = packed if packed is not None else torch.zeros(L.ACTOR_PACKED_FLOATS, dtype=torch.float32, device=dev)
+        self.lr = lr                                                                 # fp32 device scalar, shared with torch's Adam
+        self.betas, self.eps = betas, float(eps)
+        self.use_tanh, self.max_action = int(bool(use_tanh)), float(max_action)
+        self.workspace = None
+        self.net = None
+        self.adopt()
+
+    def _slices(self):
+        names = self.CRITIC_NAMES if self.critic else self.ACTOR_NAMES
+        named = dict(self.module.named_parameters())
+        off = 0
+        for k in names:
+            p = named[k]
+            yield p, off
+            off += p.numel()
+        if off != self.n:
+            raise L.SatError(f"unexpected parameter count {off} (the fused step is built for 18-256-256-{self.heads})")
+
+    def adopt(self):
+        torch = self.torch
+        with torch.no_grad():
+            for p, off in self._slices():
+                view = self.params[off:off + p.numel()].view(p.shape)
+                if p.data_ptr() != view.data_ptr():
+                    view.copy_(p.data)
+                    p.data = view
+        self.pack()
+
+    def adopted(self) -> bool:
+        return all(p.data_ptr() == self.params.data_ptr() + 4 * off for p, off in self._slices())
+
+    def bind(self, workspace):
+        self.workspace = workspace
+        self.net = L.SatPpoNet(self.params.data_ptr(), self.packed.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
+                               self.exp_avg_sq.data_ptr(), workspace.data_ptr(), self.heads, self.use_tanh, self.max_action, 0)
+
+    def pack(self):
+        if self.net is None:
+            self.bind(self.torch.zeros(4, dtype=self.torch.float32, device=self.device) if self.workspace is None else self.workspace)
+        L.check(self.lib.sat_ppo_pack(C.byref(self.net), L.stream_ptr()), "sat_ppo_pack")
+
+    def actor_weights(self):
+        """SatActorWeights over the flat buffer (for sat_actor_sample / sat_critic_forward)."""
+        b = self.params.data_ptr()
+        o3 = L.PPO_OFF_W3
+        return L.SatActorWeights(b + 4 * L.PPO_OFF_W1, b + 4 * L.PPO_OFF_B1, b + 4 * L.PPO_OFF_W2, b + 4 * L.PPO_OFF_B2,
+                                 b + 4 * o3, b + 4 * (o3 + 256 * self.heads),
+                                 None if self.critic else b + 4 * (o3 + 257 * self.heads), self.packed.data_ptr(),
+                                 18, 256, self.heads, self.use_tanh, self.max_action)
+
+    def actor_grad(self, s, a, old_logp, adv, index, mb, epsilon, entropy_coef):
+        L.check(self.lib.sat_ppo_actor_grad(C.byref(self.net), L.ptr(s), L.ptr(a), L.ptr(old_logp), L.ptr(adv), index, mb,
+                                            float(epsilon), float(entropy_coef), L.stream_ptr()), "sat_ppo_actor_grad")
+
+    def critic_grad(self, s, v_target, index, mb):
+        L.check(self.lib.sat_ppo_critic_grad(C.byref(self.net), L.ptr(s), L.ptr(v_target), index, mb, L.stream_ptr()),
+                "sat_ppo_critic_grad")
+
+    def adam(self, max_grad_norm: float, grad_scale: float = 1.0):
+        L.check(self.lib.sat_ppo_adam(C.byref(self.net), L.ptr(self.lr), self.betas[0], self.betas[1], self.eps,
+                                      float(max_grad_norm), float(grad_scale), L.ptr(self.step), L.stream_ptr()), "sat_ppo_adam")
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step.clone()}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.step.copy_(sd["step"])
+
+
+def ppo_workspace(mb: int, device):
+    torch = L.require_cuda()
+    return torch.empty(int(L.load().sat_ppo_workspace_floats(int(mb))), dtype=torch.float32, device=device)
+
+
 # --------------------------------------------------------------------------------------------- K4
 def gae_time_major(r, v, done, gamma=0.99, lamda=0.95, r_scale=None, adv=None, v_target=None):
     """r [T,N] fp32, v [T+1,N] fp32, done [T,N] uint8 (CUDA). ppo_continuous.py:198-208 per env column."""

@@ -1,0 +1,139 @@
+"""Fused PPO minibatch step (csrc/ppo_update.cu) against PyTorch autograd / torch.optim.Adam on the same
+minibatches: the oracle here is the reference's own arithmetic (ppo_continuous.py:216-239) run by PyTorch in fp32."""
+import types
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _args(use_tanh=1, clip=True, K=2, mb=512, B=1500):
+    return types.SimpleNamespace(policy_dist="Gaussian", max_action=1.6, batch_size=B, mini_batch_size=mb, max_train_steps=int(3e6),
+                                 lr_a=2e-4, lr_c=2e-4, gamma=0.99, lamda=0.95, epsilon=0.1, K_epochs=K, entropy_coef=0.01,
+                                 set_adam_eps=True, use_grad_clip=clip, use_lr_decay=True, use_adv_norm=True, state_dim=18,
+                                 action_dim=3, hidden_width=256, use_tanh=use_tanh, use_orthogonal_init=True, chkpt_dir="/tmp")
+
+
+def _pair(args, gain_boost=True):
+    from ppo_rl_satellite_b200.dropin import ppo_continuous as P
+    torch.manual_seed(0)
+    a = P.PPO_continuous(args, "pursuer")
+    b = P.PPO_continuous(args, "pursuer")
+    with torch.no_grad():
+        if gain_boost:                      # the 0.01-gain head gives near-zero means; make the policy output matter
+            a.actor.mean_layer.weight.mul_(30.0)
+            a.actor.log_std.copy_(torch.tensor([[-0.3, 0.1, 0.2]]))
+    b.actor.load_state_dict(a.actor.state_dict()); b.critic.load_state_dict(a.critic.state_dict())
+    return a, b
+
+
+def _data(agent, B, seed=1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    s = torch.randn(B, 18, device="cuda", generator=g)
+    with torch.no_grad():
+        dist = agent.actor.get_dist(s)
+        act = torch.clamp(dist.mean + dist.stddev * torch.randn(B, 3, device="cuda", generator=g), -1.6, 1.6)
+        logp = dist.log_prob(act) + 0.06 * torch.randn(B, 3, device="cuda", generator=g)      # ratios on both sides of the clip
+    adv = torch.randn(B, 1, device="cuda", generator=g)
+    vt = torch.randn(B, 1, device="cuda", generator=g)
+    return s, act, logp, adv, vt
+
+
+def _flat_grads(module, names):
+    named = dict(module.named_parameters())
+    return torch.cat([named[k].grad.reshape(-1) for k in names])
+
+
+@pytest.mark.parametrize("use_tanh,mb", [(1, 1000), (0, 1000), (1, 64), (1, 37)])
+def test_fused_gradients_match_autograd(use_tanh, mb):
+    from ppo_rl_satellite_b200 import engine as E
+    args = _args(use_tanh=use_tanh)
+    fused, eager = _pair(args)
+    B = 1500
+    s, act, logp, adv, vt = _data(eager, B)
+    index = torch.randperm(B, device="cuda")[:mb].contiguous()
+    # --- autograd (the reference's loss, :217-228 and :232-235)
+    dist_now = eager.actor.get_dist(s[index])
+    ent = dist_now.entropy().sum(1, keepdim=True)
+    ratios = torch.exp(dist_now.log_prob(act[index]).sum(1, keepdim=True) - logp[index].sum(1, keepdim=True))
+    assert ((ratios < 0.9).sum() > 0 and (ratios > 1.1).sum() > 0) or mb < 100
+    surr1 = ratios * adv[index]
+    surr2 = torch.clamp(ratios, 0.9, 1.1) * adv[index]
+    la = (-torch.min(surr1, surr2) - 0.01 * ent).mean()
+    la.backward()
+    lc = torch.nn.functional.mse_loss(vt[index], eager.critic(s[index]))
+    lc.backward()
+    # --- fused kernels
+    f = fused._fused_for(mb)
+    na, nc = f["nets"]
+    na.actor_grad(s, act, logp, adv.reshape(-1), index.data_ptr(), mb, 0.1, 0.01)
+    nc.critic_grad(s, vt.reshape(-1), index.data_ptr(), mb)
+    torch.cuda.synchronize()
+    for net, module, names, loss in ((na, eager.actor, E.PpoFusedNet.ACTOR_NAMES, la), (nc, eager.critic, E.PpoFusedNet.CRITIC_NAMES, lc)):
+        ref = _flat_grads(module, names)
+        got = net.grads[:net.n]
+        scale = ref.abs().max().item()
+        assert scale > 0
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-5 * scale + 1e-9, (err, scale)
+        assert abs(net.grads[net.n].item() - loss.item()) <= 1e-5 * max(1.0, abs(loss.item()))
+
+
+@pytest.mark.parametrize("use_tanh,clip", [(1, True), (0, False)])
+def test_fused_optimize_tracks_torch_adam(use_tanh, clip):
+    args = _args(use_tanh=use_tanh, clip=clip, K=2, mb=512)
+    fused, eager = _pair(args)
+    B = 1500
+    s, act, logp, adv, vt = _data(eager, B)
+    for it in range(2):
+        torch.manual_seed(100 + it)
+        eager.optimize(s, act, logp, adv, vt, mini_batch_size=512)
+        torch.manual_seed(100 + it)                                   # same randperm sequence
+        fused.optimize(s, act, logp, adv, vt, mini_batch_size=512, fused=True)
+    torch.cuda.synchronize()
+    assert int(fused._fused["nets"][0].step.item()) == 2 * 2 * 3       # 2 calls x K=2 x ceil(1500/512)
+    for me, mf in ((eager.actor, fused.actor), (eager.critic, fused.critic)):
+        for (k, pe), (_, pf) in zip(me.named_parameters(), mf.named_parameters()):
+            d = (pe - pf).abs()
+            assert d.max().item() <= 3e-5, (k, d.max().item())
+            assert d.mean().item() <= 2e-6, (k, d.mean().item())
+    # the parameters did move (12 Adam steps of 2e-4), so the comparison above is not vacuous
+    fresh = _pair(args)[0]
+    assert (fresh.actor.fc2.weight - fused.actor.fc2.weight).abs().mean().item() > 2e-4
+
+
+def test_fused_step_feeds_the_sampling_kernel_and_checkpoints():
+    """after a fused update the actor/critic kernels and the torch modules see the same weights"""
+    args = _args(K=1, mb=512)
+    fused, _ = _pair(args, gain_boost=False)
+    s, act, logp, adv, vt = _data(fused, 1024)
+    fused.optimize(s, act, logp, adv, vt, mini_batch_size=512, fused=True)
+    assert fused._dirty is False
+    obs = s[:200].contiguous()
+    eps = torch.zeros(200, 3, device="cuda")
+    a_k, _ = fused.actor_kernel.sample(obs=obs, eps_in=eps)
+    v_k = fused.critic_kernel.value(obs)
+    with torch.no_grad():
+        np.testing.assert_allclose(a_k.cpu().numpy(), fused.actor(obs).cpu().numpy(), atol=2e-6)
+        np.testing.assert_allclose(v_k.cpu().numpy(), fused.critic(obs).reshape(-1).cpu().numpy(), atol=5e-6)
+    # loading a checkpoint into the torch views is picked up by sync_kernels (device-side repack)
+    sd = {k: v.clone() for k, v in fused.actor.state_dict().items()}
+    sd["mean_layer.bias"] = sd["mean_layer.bias"] + 0.25
+    fused.actor.load_state_dict(sd)
+    fused._dirty = True
+    fused.sync_kernels()
+    a_k2, _ = fused.actor_kernel.sample(obs=obs, eps_in=eps)
+    with torch.no_grad():
+        np.testing.assert_allclose(a_k2.cpu().numpy(), fused.actor(obs).cpu().numpy(), atol=2e-6)
+    assert (a_k2 - a_k).abs().max().item() > 1e-3
+
+
+def test_fused_argument_errors():
+    from ppo_rl_satellite_b200 import _lib as L
+    import ctypes as C
+    lib = L.load()
+    net = L.SatPpoNet()
+    assert lib.sat_ppo_adam(C.byref(net), None, 0.9, 0.999, 1e-5, 0.5, 1.0, None, None) == -1
+    assert lib.sat_ppo_workspace_floats(0) == 0 and lib.sat_ppo_workspace_floats(64) > 74 * 65536
