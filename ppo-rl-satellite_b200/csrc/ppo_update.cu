@@ -15,7 +15,7 @@
 //                     reduced per CTA.
 //   ppo_wgrad2_kernel dW2 = dz2^T h1, split-K over 74 row slabs x 4 column blocks (296 CTAs = 2 per SM), both operands
 //                     streamed k-major through a 4-stage TMA pipeline.
-//   ppo_wgrad1_kernel dW1 = dz1^T x and db1, a streaming pass over dz1.
+//   ppo_wgrad1_kernel dW1 = dz1^T x and db1, a streaming pass over dz1 (3-stage TMA pipeline).
 //   colsum_kernel     deterministic sum of the per-CTA / per-slab partials into the flat gradient.
 //   ppo_adam_kernel   one 8-CTA cluster: gradient norm through distributed shared memory, clip, Adam, and the packed
 //                     (transposed) weight image for the next forward.
@@ -427,24 +427,63 @@ ppo_wgrad2_kernel(const float* __restrict__ dz2b, const float* __restrict__ h1g,
 }
 
 // ---------------------------------------------------------------------------------------------- dW1 = dz1^T x, db1
-__global__ void __launch_bounds__(HID)
+// A streaming pass: 16-row tiles of dz1 (16 KB, contiguous) and of the gathered observations (2 KB) arrive through a
+// 3-stage TMA pipeline; thread j owns row j of fc1.weight's gradient.
+constexpr int W1_STAGES = 3;
+struct __align__(128) W1Smem {
+    float z[W1_STAGES][KT * HID];
+    float x[W1_STAGES][KT * XS_LD];
+    uint64_t full[W1_STAGES];
+};
+
+__global__ void __launch_bounds__(HID, 4)
 ppo_wgrad1_kernel(const float* __restrict__ dz1g, const float* __restrict__ xs, int64_t mp, int slabs,
                   float* __restrict__ part_w1, float* __restrict__ part_b1) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    W1Smem& sm = *reinterpret_cast<W1Smem*>(smem_raw);
     const int j = threadIdx.x, slab = blockIdx.x;
-    const int64_t r0 = mp * slab / slabs, r1 = mp * (slab + 1) / slabs;
+    const int64_t ktiles = mp / KT;
+    const int64_t t0 = ktiles * slab / slabs, t1 = ktiles * (slab + 1) / slabs;
+    const int nt = (int)(t1 - t0);
+    const float* zsrc = dz1g + t0 * KT * HID;
+    const float* xsrc = xs + t0 * KT * XS_LD;
+    if (j == 0) {
+#pragma unroll
+        for (int st = 0; st < W1_STAGES; ++st) mbar_init(&sm.full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (j == 0) {
+        for (int st = 0; st < W1_STAGES && st < nt; ++st) {
+            mbar_expect_tx(&sm.full[st], KT * HID * 4 + KT * XS_LD * 4);
+            bulk_g2s(&sm.z[st][0], zsrc + (int64_t)st * KT * HID, KT * HID * 4, &sm.full[st]);
+            bulk_g2s(&sm.x[st][0], xsrc + (int64_t)st * KT * XS_LD, KT * XS_LD * 4, &sm.full[st]);
+        }
+    }
     float acc[IN], sb = 0.0f;
 #pragma unroll
     for (int d = 0; d < IN; ++d) acc[d] = 0.0f;
+#pragma unroll 1
+    for (int t = 0; t < nt; ++t) {
+        const int st = t % W1_STAGES;
+        mbar_wait(&sm.full[st], (t / W1_STAGES) & 1);
 #pragma unroll 4
-    for (int64_t r = r0; r < r1; ++r) {
-        const float z = dz1g[r * HID + j];
-        const float4* xr = reinterpret_cast<const float4*>(xs + r * XS_LD);
-        float x[20];
+        for (int r = 0; r < KT; ++r) {
+            const float z = sm.z[st][r * HID + j];
+            const float4* xr = reinterpret_cast<const float4*>(&sm.x[st][r * XS_LD]);
+            float x[20];
 #pragma unroll
-        for (int v = 0; v < 5; ++v) { const float4 t = __ldg(xr + v); x[v * 4] = t.x; x[v * 4 + 1] = t.y; x[v * 4 + 2] = t.z; x[v * 4 + 3] = t.w; }
-        sb += z;
+            for (int v = 0; v < 5; ++v) { const float4 q = xr[v]; x[v * 4] = q.x; x[v * 4 + 1] = q.y; x[v * 4 + 2] = q.z; x[v * 4 + 3] = q.w; }
+            sb += z;
 #pragma unroll
-        for (int d = 0; d < IN; ++d) acc[d] = fmaf(z, x[d], acc[d]);
+            for (int d = 0; d < IN; ++d) acc[d] = fmaf(z, x[d], acc[d]);
+        }
+        __syncthreads();
+        if (j == 0 && t + W1_STAGES < nt) {
+            mbar_expect_tx(&sm.full[st], KT * HID * 4 + KT * XS_LD * 4);
+            bulk_g2s(&sm.z[st][0], zsrc + (int64_t)(t + W1_STAGES) * KT * HID, KT * HID * 4, &sm.full[st]);
+            bulk_g2s(&sm.x[st][0], xsrc + (int64_t)(t + W1_STAGES) * KT * XS_LD, KT * XS_LD * 4, &sm.full[st]);
+        }
     }
     float* dst = part_w1 + (int64_t)slab * HID * IN + j * IN;       // fc1.weight layout [j][18]
 #pragma unroll
@@ -453,12 +492,13 @@ ppo_wgrad1_kernel(const float* __restrict__ dz1g, const float* __restrict__ xs, 
 }
 
 // ---------------------------------------------------------------------------------------------- partial sums -> flat gradient
+// block = 32 consecutive elements x 32 groups of partials; fixed summation order (deterministic gradients)
 struct SumGroup { const float* src; int64_t stride; int parts, elems, dst_off, block0; };
 struct SumPlan { SumGroup g[6]; int groups; };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 colsum_kernel(const SumPlan plan, float* __restrict__ grads) {
-    __shared__ float red[8][32];
+    __shared__ float red[32][33];
     int gi = 0;
 #pragma unroll
     for (int k = 1; k < 6; ++k) if (k < plan.groups && (int)blockIdx.x >= plan.g[k].block0) gi = k;
@@ -466,14 +506,17 @@ colsum_kernel(const SumPlan plan, float* __restrict__ grads) {
     const int lane = threadIdx.x & 31, ps = threadIdx.x >> 5;
     const int e = ((int)blockIdx.x - g.block0) * 32 + lane;
     float sum = 0.0f;
-    if (e < g.elems)
-        for (int p = ps; p < g.parts; p += 8) sum += g.src[(int64_t)p * g.stride + e];
+    if (e < g.elems) {
+        const float* src = g.src + e;
+#pragma unroll 8
+        for (int p = ps; p < g.parts; p += 32) sum += src[(int64_t)p * g.stride];
+    }
     red[ps][lane] = sum;
     __syncthreads();
     if (ps == 0 && e < g.elems) {
-        float t = red[0][lane];
+        float t = 0.0f;
 #pragma unroll
-        for (int k = 1; k < 8; ++k) t += red[k][lane];
+        for (int k = 0; k < 32; ++k) t += red[k][lane];
         grads[g.dst_off + e] = t;
     }
 }
@@ -583,7 +626,9 @@ int finish_grads(const SatPpoNet* net, const Workspace& w, cudaStream_t stream) 
     int rc = set_smem(ppo_wgrad2_kernel, sizeof(WgSmem));
     if (rc) return rc;
     ppo_wgrad2_kernel<<<dim3(4, slabs2), THREADS, sizeof(WgSmem), stream>>>(w.dz2b, w.h1, w.mp, slabs2, w.part_w2);
-    ppo_wgrad1_kernel<<<slabs1, HID, 0, stream>>>(w.dz1, w.xs, w.mp, slabs1, w.part_w1, w.part_b1);
+    rc = set_smem(ppo_wgrad1_kernel, sizeof(W1Smem));
+    if (rc) return rc;
+    ppo_wgrad1_kernel<<<slabs1, HID, sizeof(W1Smem), stream>>>(w.dz1, w.xs, w.mp, slabs1, w.part_w1, w.part_b1);
     SumPlan plan;
     int nb = 0, gi = 0;
     auto add = [&](const float* src, int64_t stride, int parts, int elems, int dst_off) {
@@ -597,7 +642,7 @@ int finish_grads(const SatPpoNet* net, const Workspace& w, cudaStream_t stream) 
     add(w.part_head + 3 * HID, 4 * HID, (int)w.tiles, HID, SAT_PPO_OFF_B2);
     add(w.part_scal, 8, (int)w.tiles, heads == 3 ? 7 : 2, off_b3(heads));        // db3, dlog_std, loss (one past the parameters)
     plan.groups = gi;
-    colsum_kernel<<<nb, 256, 0, stream>>>(plan, net->grads);
+    colsum_kernel<<<nb, 1024, 0, stream>>>(plan, net->grads);
     return launch_status();
 }
 

@@ -150,17 +150,18 @@ class PPO_continuous:
                                   packed=self.critic_kernel.packed, eps=eps)
             if f is not None:                         # parameters were moved (e.g. module.to()): keep the Adam moments
                 na.load_state_dict(f["nets"][0].state_dict()); nc.load_state_dict(f["nets"][1].state_dict())
-            f = self._fused = {"nets": (na, nc), "mb": 0, "ws": None}
+            f = self._fused = {"nets": (na, nc), "mb": 0, "streams": (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))}
             self.actor_kernel.w, self.critic_kernel.w = na.actor_weights(), nc.actor_weights()
             self._graph = None                        # a captured graph holds the old parameter addresses
         if f["mb"] < mb:
-            f["ws"] = _eng.ppo_workspace(mb, self.device)
             f["mb"] = mb
-            for n in f["nets"]:
-                n.bind(f["ws"])
+            for n in f["nets"]:                       # one workspace per network: the two chains run concurrently
+                n.bind(_eng.ppo_workspace(mb, self.device))
         return f
 
     def _optimize_fused(self, s, a, a_logprob, adv, v_target, mb, group):
+        """The actor chain and the critic chain are independent (ppo_continuous.py:216-239 shares only s[index]), so each
+        runs on its own stream: one network's short kernels (partial sums, Adam) hide under the other's GEMM kernels."""
         dist = torch.distributed
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         B = s.shape[0]
@@ -169,41 +170,27 @@ class PPO_continuous:
         s, a, a_logprob = s.contiguous(), a.contiguous(), a_logprob.contiguous()
         adv, v_target = adv.reshape(-1).contiguous(), v_target.reshape(-1).contiguous()
         clip = 0.5 if self.use_grad_clip else 0.0
+        main = torch.cuda.current_stream(self.device)
+        sa, sc = f["streams"]
         for _ in range(self.K_epochs):
             perm = torch.randperm(B, device=s.device)
+            sa.wait_stream(main); sc.wait_stream(main)
+            perm.record_stream(sa); perm.record_stream(sc)
             for lo in range(0, B, mb):
                 m = min(mb, B - lo)
                 index = perm.data_ptr() + 8 * lo
-                na.actor_grad(s, a, a_logprob, adv, index, m, self.epsilon, self.entropy_coef)
-                if world > 1:
-                    dist.all_reduce(na.grads, group=group)
-                na.adam(clip, 1.0 / world)
-                nc.critic_grad(s, v_target, index, m)
-                if world > 1:
-                    dist.all_reduce(nc.grads, group=group)
-                nc.adam(clip, 1.0 / world)
+                with torch.cuda.stream(sa):
+                    na.actor_grad(s, a, a_logprob, adv, index, m, self.epsilon, self.entropy_coef)
+                    if world > 1:
+                        dist.all_reduce(na.grads, group=group)
+                    na.adam(clip, 1.0 / world)
+                with torch.cuda.stream(sc):
+                    nc.critic_grad(s, v_target, index, m)
+                    if world > 1:
+                        dist.all_reduce(nc.grads, group=group)
+                    nc.adam(clip, 1.0 / world)
+        main.wait_stream(sa); main.wait_stream(sc)
         self._dirty = False                           # the Adam kernel rewrites the packed weight images itself
-
-    def _obs(self, s):
-        a = np.asarray(s, dtype=np.float32)
-        return torch.as_tensor(np.ascontiguousarray(a.reshape(-1, a.shape[-1])), device=self.device), a.ndim == 1
-
-    def evaluate(self, s):
-        x, one = self._obs(s)
-        with torch.no_grad():
-            a = self.actor(x).cpu().numpy()
-        return a.flatten() if one else a
-
-    def choose_action(self, s):
-        """(a, a_logprob) as float32 numpy, flattened for a single observation (ppo_continuous.py:176-189)."""
-        if self._dirty:
-            self.sync_kernels()
-        x, one = self._obs(s)
-        a, lp = self.actor_kernel.sample(obs=x, seed=self.seed, step=self._step)
-        self._step += 1
-        out = torch.cat([a, lp], dim=1).cpu().numpy()
-        a, lp = out[:, :a.shape[1]], out[:, a.shape[1]:]
-        return (a.flatten(), lp.flatten()) if one else (a, lp)
 
     # ---- PPO update
     def update(self, replay_buffer, total_steps):
