@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--ppo-envs", type=int, default=8192, help="envs per GPU of the PPO section (config 5: 65536/8)")
     ap.add_argument("--ppo-minibatch", type=int, default=65536, help="samples per GPU per optimiser step")
     ap.add_argument("--ppo-eager", action="store_true", help="run the optimiser steps eagerly instead of as a CUDA graph")
+    ap.add_argument("--ppo-update", choices=("fused", "torch"), default="fused",
+                    help="optimiser step: hand-written forward/backward/Adam kernels, or the PyTorch step (CUDA-graphed)")
     ap.add_argument("--cpu-sample-envs", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
     return ap.parse_args()
 
@@ -196,10 +198,11 @@ def run_ppo_section(args, rank, world, dev, torch, dist, eng):
             dist.barrier()
         torch.cuda.synchronize()
     use_graph = not args.ppo_eager and (world == 1 or os.environ.get("SAT_GRAPH_DDP", "1") == "1")
-    tr.collect(); tr.update(mb, group=group, use_graph=use_graph)     # warm-up iteration (cuBLAS handles, graph capture)
+    fused = args.ppo_update == "fused"
+    tr.collect(); tr.update(mb, group=group, use_graph=use_graph, fused=fused)     # warm-up iteration (workspaces, graph capture)
     sync()
     t0 = time.perf_counter(); tr.collect(); sync(); t1 = time.perf_counter()
-    tr.update(mb, total_steps=1, group=group, use_graph=use_graph); sync(); t2 = time.perf_counter()
+    tr.update(mb, total_steps=1, group=group, use_graph=use_graph, fused=fused); sync(); t2 = time.perf_counter()
     dt = torch.tensor([t1 - t0, t2 - t1], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -208,7 +211,8 @@ def run_ppo_section(args, rank, world, dev, torch, dist, eng):
     return {"ppo_samples_per_sec": samples / (tc + tu), "rollout_s": tc, "update_s": tu, "samples": samples,
             "config": f"T={T} x {n} envs/GPU (rk4 mode, S={args.substeps}), minibatch {mb}/GPU, K=10, gamma .99, lambda .95 "
                       f"(CPPO_main.py:24-27); config 5 proper is --ppo-horizon 2048 --ppo-envs 8192 on 8 GPUs",
-            "optimizer_steps": 10 * -(-T * n // mb), "cuda_graph": bool(use_graph and agent._graph is not None), "allreduce": "NCCL, 2 flat buckets (286 KB + 284 KB) per step" if world > 1 else None,
+            "optimizer_steps": 10 * -(-T * n // mb), "update_impl": "fused CUDA kernels (csrc/ppo_update.cu), actor and critic chains on two streams" if fused else "PyTorch autograd + torch.optim.Adam",
+            "cuda_graph": bool(not fused and use_graph and agent._graph is not None), "allreduce": "NCCL, 2 flat buckets (286 KB + 284 KB) per step" if world > 1 else None,
             "timing": "wall clock with barrier + synchronize on both sides, max over ranks"}
 
 

@@ -4,8 +4,9 @@ Same classes, parameter names and checkpoint files as the reference, so model_fi
 unchanged (ppo_continuous.py:61-134, 252-258):
   choose_action -> fused Gaussian-actor kernel (forward + Philox sampling + log-prob), batch 1 or [N, 18]
   update        -> critic values, sat_gae_flat reverse scan, advantage normalisation kernel; the K-epoch clipped-PPO
-                   minibatch loop stays PyTorch on the GPU with a gradient all-reduce when
-                   torch.distributed is initialised (one flat bucket per network, NCCL over NVLink).
+                   minibatch loop runs on the fused forward/backward/Adam kernels of csrc/ppo_update.cu (fused_update=True,
+                   SURVEY s8 f.1) or as the PyTorch step, with a gradient all-reduce when torch.distributed is
+                   initialised (one flat bucket per network, NCCL over NVLink).
 Only the Gaussian policy is on the CUDA path (policy_dist == "Beta" is out of the north star's scope).
 """
 import os
@@ -103,7 +104,7 @@ def allreduce_grads_(module, group=None):
 
 
 class PPO_continuous:
-    def __init__(self, args, agent_idx, device="cuda", seed=0):
+    def __init__(self, args, agent_idx, device="cuda", seed=0, fused_update=True):
         if getattr(args, "policy_dist", "Gaussian") != "Gaussian":
             raise NotImplementedError("only the Gaussian policy is on the CUDA path")
         self.device = torch.device(device)
@@ -122,6 +123,7 @@ class PPO_continuous:
         self.optimizer_critic = torch.optim.Adam(self.critic.parameters(), lr=torch.tensor(float(self.lr_c), device=self.device), **eps, **cap)
         self._graph = None
         self._fused = None
+        self.fused_update = bool(fused_update)        # update(): fused CUDA minibatch step instead of autograd + torch Adam
         self._use_tanh = bool(args.use_tanh)
         self.actor_kernel = _eng.GaussianActorKernel(max_action=self.max_action, use_tanh=self._use_tanh, device=self.device)
         self.critic_kernel = _eng.GaussianActorKernel(use_tanh=self._use_tanh, device=self.device, critic=True)
@@ -153,6 +155,9 @@ class PPO_continuous:
             f = self._fused = {"nets": (na, nc), "mb": 0, "streams": (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))}
             self.actor_kernel.w, self.critic_kernel.w = na.actor_weights(), nc.actor_weights()
             self._graph = None                        # a captured graph holds the old parameter addresses
+        # torch's Optimizer.load_state_dict replaces the lr tensors: always read the live ones
+        f["nets"][0].lr = self.optimizer_actor.param_groups[0]["lr"]
+        f["nets"][1].lr = self.optimizer_critic.param_groups[0]["lr"]
         if f["mb"] < mb:
             f["mb"] = mb
             for n in f["nets"]:                       # one workspace per network: the two chains run concurrently
@@ -192,6 +197,27 @@ class PPO_continuous:
         main.wait_stream(sa); main.wait_stream(sc)
         self._dirty = False                           # the Adam kernel rewrites the packed weight images itself
 
+    def _obs(self, s):
+        a = np.asarray(s, dtype=np.float32)
+        return torch.as_tensor(np.ascontiguousarray(a.reshape(-1, a.shape[-1])), device=self.device), a.ndim == 1
+
+    def evaluate(self, s):
+        x, one = self._obs(s)
+        with torch.no_grad():
+            a = self.actor(x).cpu().numpy()
+        return a.flatten() if one else a
+
+    def choose_action(self, s):
+        """(a, a_logprob) as float32 numpy, flattened for a single observation (ppo_continuous.py:176-189)."""
+        if self._dirty:
+            self.sync_kernels()
+        x, one = self._obs(s)
+        a, lp = self.actor_kernel.sample(obs=x, seed=self.seed, step=self._step)
+        self._step += 1
+        out = torch.cat([a, lp], dim=1).cpu().numpy()
+        a, lp = out[:, :a.shape[1]], out[:, a.shape[1]:]
+        return (a.flatten(), lp.flatten()) if one else (a, lp)
+
     # ---- PPO update
     def update(self, replay_buffer, total_steps):
         s, a, a_logprob, r, s_, dw, done = (t.to(self.device) for t in replay_buffer.numpy_to_tensor())
@@ -201,7 +227,7 @@ class PPO_continuous:
             adv, v_target = adv.view(-1, 1), v_target.view(-1, 1)
             if self.use_adv_norm:
                 _eng.adv_normalize_(adv, group=False)
-        self.optimize(s, a, a_logprob, adv, v_target)
+        self.optimize(s, a, a_logprob, adv, v_target, fused=self.fused_update)
         if self.use_lr_decay:
             self.lr_decay(total_steps)
 

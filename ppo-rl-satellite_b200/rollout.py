@@ -2,8 +2,8 @@
 
 Per step: pursuer actor kernel (observation rebuilt + normalised from the fp64 state, Philox sample) -> evader actor
 kernel -> fused env step (statistics updated in-kernel). After T steps: critic values, time-major GAE kernel,
-advantage normalisation with all-reduced moments, then the K-epoch minibatch update (PyTorch + NCCL gradient
-all-reduce). Envs shard across ranks with no traffic during the rollout."""
+advantage normalisation with all-reduced moments, then the K-epoch minibatch update (fused forward/backward/Adam kernels,
+or the PyTorch step, + NCCL gradient all-reduce). Envs shard across ranks with no traffic during the rollout."""
 from __future__ import annotations
 
 import torch
@@ -83,15 +83,18 @@ class VectorTrainer:
             eng.adv_normalize_(buf.adv, group=group)
         return buf.adv, buf.v_target
 
-    def update(self, mini_batch_size: int, total_steps: int = 0, group=None, use_graph: bool = True):
+    def update(self, mini_batch_size: int, total_steps: int = 0, group=None, use_graph: bool = True, fused: bool = True):
+        """fused: hand-written forward/backward/Adam kernels (csrc/ppo_update.cu); otherwise the PyTorch step, replayed as
+        a CUDA graph when use_graph."""
         buf, ag = self.buf, self.agent
         adv, v_target = self.compute_advantages(group)
         B = self.T * self.env.n
         ag.optimize(buf.obs[:self.T].reshape(B, 18), buf.act.reshape(B, 3), buf.logp.reshape(B, 3), adv.reshape(B, 1),
-                    v_target.reshape(B, 1), mini_batch_size=mini_batch_size, group=group, use_graph=use_graph)
+                    v_target.reshape(B, 1), mini_batch_size=mini_batch_size, group=group, use_graph=use_graph, fused=fused)
         if ag.use_lr_decay:
             ag.lr_decay(total_steps)
-        ag.sync_kernels()
+        if ag._dirty:
+            ag.sync_kernels()
 
 
     # ---- full-run checkpoint: env SoA state, running normalisers, Philox counter, networks + optimisers
@@ -102,6 +105,7 @@ class VectorTrainer:
                 "ret_stats": self.ret_stats.state_dict() if self.ret_stats is not None else None,
                 "actor": ag.actor.state_dict(), "critic": ag.critic.state_dict(),
                 "opt_actor": ag.optimizer_actor.state_dict(), "opt_critic": ag.optimizer_critic.state_dict(),
+                "fused_adam": [n.state_dict() for n in ag._fused["nets"]] if ag._fused is not None else None,
                 "opponent_actor": self.opponent.actor.state_dict()}
 
     def load_state_dict(self, sd):
@@ -115,6 +119,9 @@ class VectorTrainer:
         ag.actor.load_state_dict(sd["actor"]); ag.critic.load_state_dict(sd["critic"])
         ag.optimizer_actor.load_state_dict(sd["opt_actor"]); ag.optimizer_critic.load_state_dict(sd["opt_critic"])
         self.opponent.actor.load_state_dict(sd["opponent_actor"])
+        if sd.get("fused_adam") is not None:
+            for n, st in zip(ag._fused_for(1)["nets"], sd["fused_adam"]):
+                n.load_state_dict(st)
         ag.sync_kernels(); self.opponent.sync_kernels()
         return self
 
@@ -130,7 +137,7 @@ class SelfPlay:
         self.trainers = {0: VectorTrainer(env, pursuer, evader, T, rank=rank, seed=seed, **kw),
                          1: VectorTrainer(env, evader, pursuer, T, rank=rank, seed=seed + 1, **kw)}
 
-    def run_phase(self, flag: int, iterations: int, group=None, use_graph: bool = True, callback=None):
+    def run_phase(self, flag: int, iterations: int, group=None, use_graph: bool = True, fused: bool = True, callback=None):
         env, tr = self.env, self.trainers[flag]
         env.reset(flag=flag)                                   # reset(Flag) for every env; fuel / dis / dz persist (Q2)
         tr.learner_is_pursuer = flag == 0
@@ -139,7 +146,7 @@ class SelfPlay:
             tr.collect()
             stats = {"flag": flag, "iteration": it, "mean_reward": float(tr.buf.rew64.mean()),
                      "episodes_finished": int(tr.buf.done.sum())}
-            tr.update(self.mb, total_steps=it, group=group, use_graph=use_graph)
+            tr.update(self.mb, total_steps=it, group=group, use_graph=use_graph, fused=fused)
             out.append(stats)
             if callback is not None:
                 callback(stats)

@@ -1,5 +1,6 @@
 """Fused PPO minibatch step (csrc/ppo_update.cu) against PyTorch autograd / torch.optim.Adam on the same
 minibatches: the oracle here is the reference's own arithmetic (ppo_continuous.py:216-239) run by PyTorch in fp32."""
+import copy
 import types
 
 import numpy as np
@@ -137,3 +138,30 @@ def test_fused_argument_errors():
     net = L.SatPpoNet()
     assert lib.sat_ppo_adam(C.byref(net), None, 0.9, 0.999, 1e-5, 0.5, 1.0, None, None) == -1
     assert lib.sat_ppo_workspace_floats(0) == 0 and lib.sat_ppo_workspace_floats(64) > 74 * 65536
+
+
+def test_vector_trainer_fused_update_resumes_exactly(tmp_path):
+    """full-run checkpoint (env state, normalisers, Philox counter, weights, fused Adam moments + step): the resumed run
+    reproduces the uninterrupted one bit for bit (the fused step sums in a fixed order)"""
+    from ppo_rl_satellite_b200 import engine as eng, rollout
+    from ppo_rl_satellite_b200.dropin import ppo_continuous as P
+    n, T, mb = 256, 8, 512
+
+    def make():
+        torch.manual_seed(0)
+        args = _args(K=2, mb=mb, B=n * T)
+        env = eng.EnvBatch(n, mode="cw", d_capture=20000.0, max_episode_steps=5, auto_reset=True)
+        agent, opp = P.PPO_continuous(args, "pursuer"), P.PPO_continuous(args, "evader")
+        return rollout.VectorTrainer(env, agent, opp, T)
+
+    a = make()
+    a.collect(); torch.manual_seed(5); a.update(mb, total_steps=1000)
+    sd = copy.deepcopy(a.state_dict())            # module state_dicts alias the live parameters
+    assert sd["fused_adam"] is not None and int(sd["fused_adam"][0]["step"].item()) == 2 * 4
+    a.collect(); torch.manual_seed(6); a.update(mb, total_steps=2000)
+    b = make().load_state_dict(sd)
+    b.collect(); torch.manual_seed(6); b.update(mb, total_steps=2000)
+    for pa, pb in zip(list(a.agent.actor.parameters()) + list(a.agent.critic.parameters()),
+                      list(b.agent.actor.parameters()) + list(b.agent.critic.parameters())):
+        assert torch.equal(pa, pb)
+    assert torch.equal(a.buf.act, b.buf.act) and torch.equal(a.buf.rew64, b.buf.rew64)
