@@ -1,6 +1,7 @@
 """Fused PPO minibatch step (csrc/ppo_update.cu) against PyTorch autograd / torch.optim.Adam on the same
 minibatches: the oracle here is the reference's own arithmetic (ppo_continuous.py:216-239) run by PyTorch in fp32."""
 import copy
+import os
 import types
 
 import numpy as np
@@ -165,3 +166,49 @@ def test_vector_trainer_fused_update_resumes_exactly(tmp_path):
                       list(b.agent.actor.parameters()) + list(b.agent.critic.parameters())):
         assert torch.equal(pa, pb)
     assert torch.equal(a.buf.act, b.buf.act) and torch.equal(a.buf.rew64, b.buf.rew64)
+
+
+# ---------------------------------------------------------------- two ranks (gloo carrying CUDA tensors, both on cuda:0)
+def _rank_worker(rank, world, port, q):
+    import os, sys
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        args = _args(K=3, mb=512, B=512)
+        agent, _ = _pair(args)
+        s, act, logp, adv, vt = _data(agent, 1024)                    # same 1024 rows on both ranks; each trains on its half
+        lo = rank * 512
+        agent.optimize(s[lo:lo + 512], act[lo:lo + 512], logp[lo:lo + 512], adv[lo:lo + 512], vt[lo:lo + 512],
+                       mini_batch_size=512, fused=True)
+        torch.cuda.synchronize()
+        flat = torch.cat([p.detach().reshape(-1) for p in list(agent.actor.parameters()) + list(agent.critic.parameters())])
+        q.put((rank, flat.cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_average_gradients_like_one_rank_on_the_union():
+    """world 2, one full-batch step per epoch: averaging the two ranks' mean-gradients == the gradient of the union batch,
+    so both ranks must end on the parameters a single process reaches with the 1024-row batch."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_rank_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert np.array_equal(res[0], res[1])                              # replicas stay identical
+    args = _args(K=3, mb=1024, B=1024)
+    agent, _ = _pair(args)
+    s, act, logp, adv, vt = _data(agent, 1024)
+    agent.optimize(s, act, logp, adv, vt, mini_batch_size=1024, fused=True)
+    one = torch.cat([p.detach().reshape(-1) for p in list(agent.actor.parameters()) + list(agent.critic.parameters())]).cpu().numpy()
+    assert np.abs(res[0] - one).max() <= 3e-5 and np.abs(res[0] - one).mean() <= 2e-6
+    assert np.abs(one - torch.cat([p.detach().reshape(-1) for p in list(_pair(args)[0].actor.parameters())
+                                   + list(_pair(args)[0].critic.parameters())]).cpu().numpy()).mean() > 1e-4
