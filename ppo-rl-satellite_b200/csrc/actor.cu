@@ -6,11 +6,11 @@
 //     a  = clamp(mean + exp(log_std) * eps, -max_action, max_action); logp = Normal(mean, std).log_prob(a)
 //
 // fp32 CUDA-core FFMA by design (the reference computes in fp32 and the north star rules tensor cores
-// out for this path). One CTA = 64 observations x 128 threads, each thread an 8 x 16 register tile.
+// out for this path). One CTA = 64 observations, each thread an 8 x CT register tile (mlp_tile.cuh).
 // h1 stays in shared memory (transposed, [256][64+4]); W2^T (256 KB, larger than smem) is streamed
 // through two 16 KB stages with TMA bulk copies (cp.async.bulk + mbarrier) from the pre-packed,
-// L2-resident weight buffer. 2 CTAs per SM (112 KB smem each); 65 536 observations -> 1024 CTAs =
-// 6.9 per SM.
+// L2-resident weight buffer. 2 CTAs per SM (112 KB smem each, 256 threads with the 8 x 8 tile); 65 536 observations
+// -> 1024 CTAs = 6.9 per SM.
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "sat_math.cuh"
@@ -29,7 +29,7 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
              float* __restrict__ eps_out, float* __restrict__ obs_out, float* __restrict__ v_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
     const int64_t row0 = (int64_t)blockIdx.x * M;
     const int heads = CRITIC ? 1 : 3;
 
@@ -80,18 +80,18 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
     }
 
     // ---------------- layer 1: h1 = act(W1 x + b1) -> h1T
-    float2 acc[RT][8];
+    float2 acc[RT][NP];
 #pragma unroll
     for (int i = 0; i < RT; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
+        for (int j = 0; j < NP; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
     mbar_wait(&sm.bar_misc, 0);
     tile_fma<IN>(acc, sm.xT, M, &sm.wt[0][0], ty, tx);
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int j = c * 64 + tx * 4 + q;
+            const int j = c * CSTR + tx * 4 + q;
             const float bias = __ldg(packed + OFF_B1 + j);
 #pragma unroll
             for (int i4 = 0; i4 < RT / 4; ++i4) {
@@ -115,7 +115,7 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
 #pragma unroll
     for (int i = 0; i < RT; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
+        for (int j = 0; j < NP; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
 #pragma unroll 1
     for (int t = 0; t < NT; ++t) {
         const int s = t & 1;
@@ -133,10 +133,10 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
 #pragma unroll
     for (int i = 0; i < RT; ++i) { part[i][0] = 0.0f; part[i][1] = 0.0f; part[i][2] = 0.0f; }
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int j = c * 64 + tx * 4 + q;
+            const int j = c * CSTR + tx * 4 + q;
             const float bias = __ldg(packed + OFF_B2 + j);
             float w[3];
 #pragma unroll
@@ -149,7 +149,7 @@ actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
             }
         }
 #pragma unroll
-    for (int off = 1; off < 16; off <<= 1)
+    for (int off = 1; off < TXN; off <<= 1)
 #pragma unroll
         for (int i = 0; i < RT; ++i)
 #pragma unroll

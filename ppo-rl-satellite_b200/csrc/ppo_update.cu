@@ -71,18 +71,18 @@ struct __align__(128) FbSmem {
     uint64_t full[NSTAGE];
     uint64_t bar_misc;
 };
-static_assert(4 * 4 * HID * 4 <= NSTAGE * KT * HID * 4, "reduction scratch must fit in the stage region");
+static_assert(NWARPS * 4 * HID * 4 <= NSTAGE * KT * HID * 4, "reduction scratch must fit in the stage region");
 
 __device__ __forceinline__ float act_grad(float h, int use_tanh) { return use_tanh ? 1.0f - h * h : (h > 0.0f ? 1.0f : 0.0f); }
-__device__ __forceinline__ float& acc_ref(float2 (&acc)[RT][8], int i, int c, int q) {
+__device__ __forceinline__ float& acc_ref(float2 (&acc)[RT][NP], int i, int c, int q) {
     float2& v = acc[i][c * 2 + (q >> 1)];
     return (q & 1) ? v.y : v.x;
 }
-__device__ __forceinline__ void acc_zero(float2 (&acc)[RT][8]) {
+__device__ __forceinline__ void acc_zero(float2 (&acc)[RT][NP]) {
 #pragma unroll
     for (int i = 0; i < RT; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
+        for (int j = 0; j < NP; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
 }
 
 template <bool CRITIC>
@@ -93,10 +93,9 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
               int64_t n, float inv_n, float epsilon, float entropy_coef,
               float* __restrict__ h1g, float* __restrict__ dz2b, float* __restrict__ dz1g, float* __restrict__ xs,
               float* __restrict__ part_head, float* __restrict__ part_scal, int64_t mp) {
-    static_assert(RT == 8, "the backward tile is written for the 8 x 16 register tile");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FbSmem& sm = *reinterpret_cast<FbSmem*>(smem_raw);
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, warp = tid >> 5;
+    const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN, warp = tid >> 5;
     const int64_t row0 = (int64_t)blockIdx.x * M;
     constexpr int heads = CRITIC ? 1 : 3;
 
@@ -126,15 +125,15 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
     }
 
     // ---------------- layer 1
-    float2 acc[RT][8];
+    float2 acc[RT][NP];
     acc_zero(acc);
     mbar_wait(&sm.bar_misc, 0);
     tile_fma<IN>(acc, sm.xT, M, &sm.wt[0][0], ty, tx);
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int j = c * 64 + tx * 4 + q;
+            const int j = c * CSTR + tx * 4 + q;
             const float bias = __ldg(packed + OFF_B1 + j);
 #pragma unroll
             for (int i = 0; i < RT; ++i) acc_ref(acc, i, c, q) = activate(acc_ref(acc, i, c, q) + bias, use_tanh);
@@ -150,9 +149,9 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
 #pragma unroll
     for (int i = 0; i < RT; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
             const float2 lo = acc[i][c * 2], hi = acc[i][c * 2 + 1];
-            *reinterpret_cast<float4*>(h1g + (row0 + ty * RT + i) * HID + c * 64 + tx * 4) = make_float4(lo.x, lo.y, hi.x, hi.y);
+            *reinterpret_cast<float4*>(h1g + (row0 + ty * RT + i) * HID + c * CSTR + tx * 4) = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
     __syncthreads();      // h1T complete; W1^T region free for the W2^T stages
 
@@ -186,10 +185,10 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
 #pragma unroll
             for (int h = 0; h < heads; ++h) part[i][h] = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int j = c * 64 + tx * 4 + q;
+                const int j = c * CSTR + tx * 4 + q;
                 const float bias = __ldg(packed + OFF_B2 + j);
                 float w[heads];
 #pragma unroll
@@ -203,7 +202,7 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
                 }
             }
 #pragma unroll
-        for (int off = 1; off < 16; off <<= 1)
+        for (int off = 1; off < TXN; off <<= 1)
 #pragma unroll
             for (int i = 0; i < RT; ++i)
 #pragma unroll
@@ -280,12 +279,12 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
         for (int i = 0; i < RT; ++i)
 #pragma unroll
             for (int h = 0; h < heads; ++h) d3[i][h] = sm.dz3[(ty * RT + i) * ACTP + h];
-        float* scratch = &sm.wt[0][0];                       // [4 warps][4 rows][HID]
+        float* scratch = &sm.wt[0][0];                       // [NWARPS][4 rows][HID]
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int j = c * 64 + tx * 4 + q;
+                const int j = c * CSTR + tx * 4 + q;
                 float w[heads], sw[heads], sb = 0.0f;
 #pragma unroll
                 for (int h = 0; h < heads; ++h) { w[h] = sm.w3[h * HID + j]; sw[h] = 0.0f; }
@@ -300,9 +299,12 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
                     acc_ref(acc, i, c, q) = dz;
                 }
 #pragma unroll
-                for (int h = 0; h < heads; ++h) sw[h] += __shfl_xor_sync(0xffffffffu, sw[h], 16);
-                sb += __shfl_xor_sync(0xffffffffu, sb, 16);
-                if ((tid & 16) == 0) {
+                if (TXN == 16) {                             // two row groups share a warp
+#pragma unroll
+                    for (int h = 0; h < heads; ++h) sw[h] += __shfl_xor_sync(0xffffffffu, sw[h], 16);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, 16);
+                }
+                if ((tid & 31) < TXN) {
 #pragma unroll
                     for (int h = 0; h < heads; ++h) scratch[(warp * 4 + h) * HID + j] = sw[h];
                     scratch[(warp * 4 + 3) * HID + j] = sb;
@@ -319,9 +321,10 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
 #pragma unroll
         for (int i = 0; i < RT; ++i)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < NC; ++c) {
                 const float2 lo = acc[i][c * 2], hi = acc[i][c * 2 + 1];
-                *reinterpret_cast<float4*>(dz2b + ((int64_t)c * mp + row0 + ty * RT + i) * 64 + tx * 4) = make_float4(lo.x, lo.y, hi.x, hi.y);
+                const int j0 = c * CSTR + tx * 4;
+                *reinterpret_cast<float4*>(dz2b + ((int64_t)(j0 >> 6) * mp + row0 + ty * RT + i) * 64 + (j0 & 63)) = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
     }
     __syncthreads();
@@ -330,8 +333,12 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
         float* dst = part_head + (int64_t)blockIdx.x * 4 * HID;
         for (int e = tid; e < 4 * HID; e += THREADS) {
             const int r = e / HID;
-            if (r < heads || r == 3)
-                dst[e] = (scratch[e] + scratch[4 * HID + e]) + (scratch[8 * HID + e] + scratch[12 * HID + e]);
+            if (r < heads || r == 3) {
+                float t = scratch[e];
+#pragma unroll
+                for (int w = 1; w < NWARPS; ++w) t += scratch[w * 4 * HID + e];
+                dst[e] = t;
+            }
         }
     }
     __syncthreads();      // scratch consumed, dz2^T complete
@@ -360,8 +367,8 @@ ppo_fb_kernel(const float* __restrict__ packed, const float* __restrict__ w2, in
 #pragma unroll
     for (int i = 0; i < RT; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int64_t o = (row0 + ty * RT + i) * HID + c * 64 + tx * 4;
+        for (int c = 0; c < NC; ++c) {
+            const int64_t o = (row0 + ty * RT + i) * HID + c * CSTR + tx * 4;
             const float4 hv = *reinterpret_cast<const float4*>(h1g + o);
             const float2 lo = acc[i][c * 2], hi = acc[i][c * 2 + 1];
             *reinterpret_cast<float4*>(dz1g + o) = make_float4(lo.x * act_grad(hv.x, use_tanh), lo.y * act_grad(hv.y, use_tanh),
@@ -382,7 +389,7 @@ ppo_wgrad2_kernel(const float* __restrict__ dz2b, const float* __restrict__ h1g,
                   float* __restrict__ part_w2) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw);
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
     const int jb = blockIdx.x, slab = blockIdx.y;
     const int64_t ktiles = mp / KT;
     const int64_t t0 = ktiles * slab / slabs, t1 = ktiles * (slab + 1) / slabs;
@@ -402,7 +409,7 @@ ppo_wgrad2_kernel(const float* __restrict__ dz2b, const float* __restrict__ h1g,
             bulk_g2s(&sm.b[st][0], bsrc + (int64_t)st * KT * HID, KT * HID * 4, &sm.full[st]);
         }
     }
-    float2 acc[RT][8];
+    float2 acc[RT][NP];
     acc_zero(acc);
 #pragma unroll 1
     for (int t = 0; t < nt; ++t) {
@@ -420,9 +427,9 @@ ppo_wgrad2_kernel(const float* __restrict__ dz2b, const float* __restrict__ h1g,
 #pragma unroll
     for (int i = 0; i < RT; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
             const float2 lo = acc[i][c * 2], hi = acc[i][c * 2 + 1];
-            *reinterpret_cast<float4*>(dst + (int64_t)(jb * 64 + ty * RT + i) * HID + c * 64 + tx * 4) = make_float4(lo.x, lo.y, hi.x, hi.y);
+            *reinterpret_cast<float4*>(dst + (int64_t)(jb * 64 + ty * RT + i) * HID + c * CSTR + tx * 4) = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
 }
 
