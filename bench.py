@@ -35,6 +35,9 @@ FLOP_ENV_STEP = 34800.0        # 2 craft x 100 substeps x 174 FLO
 FLOP_RK4_J2 = 174.0
 FP64_INSTR_RK4_J2 = 106.5      # DFMA+DMUL+DADD per RK4+J2 step in the SASS of rk4_kernel<true,2> (cuobjdump)
 FLOP_ACTOR = 141824.0          # fp32 per actor forward
+# one sample through one PPO optimiser step (both networks): forward 141 824 + 140 800, backward through fc2 2 x 131 072,
+# weight gradients 2 x 2 x (256 x 256 + 18 x 256) + heads  
+FLOP_PPO_SAMPLE_STEP = (141824.0 + 140800.0) + 2 * 131072.0 + 2 * 2 * (65536.0 + 4608.0) + 2 * 4 * 256.0
 BYTES_ENV_STEP = 345.0
 
 
@@ -394,6 +397,11 @@ def run_ours(args, rank, world, local_rank):
     ppo = None
     if not args.no_ppo:
         ppo = run_ppo_section(args, rank, world, dev, torch, dist, eng)
+        per_gpu_sample_steps = ppo["samples"] / world * 10
+        ppo["optimizer_step_ms"] = 1e3 * ppo["update_s"] / ppo["optimizer_steps"]
+        ppo["update_fp32_tflops_per_gpu"] = FLOP_PPO_SAMPLE_STEP * per_gpu_sample_steps / ppo["update_s"] / 1e12
+        ppo["update_frac_of_measured_fp32_peak"] = ppo["update_fp32_tflops_per_gpu"] / peak32
+        ppo["update_flops_per_sample_step"] = FLOP_PPO_SAMPLE_STEP
     clocks = sampler.stop() if rank == 0 else None     # sampled from warm-up to the end of every GPU-timed section
 
     if rank != 0:
