@@ -215,7 +215,10 @@ def run_ppo_section(args, rank, world, dev, torch, dist, eng):
             "config": f"T={T} x {n} envs/GPU (rk4 mode, S={args.substeps}), minibatch {mb}/GPU, K=10, gamma .99, lambda .95 "
                       f"(CPPO_main.py:24-27); config 5 proper is --ppo-horizon 2048 --ppo-envs 8192 on 8 GPUs",
             "optimizer_steps": 10 * -(-T * n // mb), "update_impl": "fused CUDA kernels (csrc/ppo_update.cu), actor and critic chains on two streams" if fused else "PyTorch autograd + torch.optim.Adam",
-            "cuda_graph": bool(not fused and use_graph and agent._graph is not None), "allreduce": "NCCL, 2 flat buckets (286 KB + 284 KB) per step" if world > 1 else None,
+            "cuda_graph": bool(not fused and use_graph and agent._graph is not None), "allreduce": None if world == 1 else (
+                "fused into the Adam kernel: every rank reads all ranks' flat gradients (286 KB + 284 KB) from NVLink peer memory "
+                "(torch symmetric memory) in rank order after a device-side barrier; no NCCL call on the step"
+                if fused and agent._fused is not None and agent._fused.get("peers") else "NCCL, 2 flat buckets (286 KB + 284 KB) per step"),
             "timing": "wall clock with barrier + synchronize on both sides, max over ranks"}
 
 

@@ -267,6 +267,14 @@ int sat_ppo_critic_grad(const SatPpoNet* net, const float* s, const float* v_tar
  * the learning rate read from device memory (*lr) and the step counter *step (device, incremented here) */
 int sat_ppo_adam(const SatPpoNet* net, const float* lr, float beta1, float beta2, float eps, float max_grad_norm,
                  float grad_scale, int64_t* step, void* stream);
+/* The same step with the gradient all-reduce fused in (multi-GPU, SURVEY.md s8e exchange step 1): peer_grads is a DEVICE
+ * array of `world` pointers to every rank's flat gradient buffer mapped into this process (NVLink peer memory, e.g. a
+ * torch symmetric-memory allocation); the kernel reads peer_grads[r][offset_floats + i] for all r in rank order, so all
+ * replicas compute bit-identical sums. The caller orders the ranks with a device-side barrier between the gradient
+ * kernels and this call and alternates offset_floats between two halves of the buffer from step to step. */
+int sat_ppo_adam_peers(const SatPpoNet* net, const float* lr, float beta1, float beta2, float eps, float max_grad_norm,
+                       float grad_scale, int64_t* step, const float* const* peer_grads, int world, int64_t offset_floats,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): dependent-free DFMA / FFMA chains to measure the FP64 / FP32

@@ -71,6 +71,7 @@ SIGNATURES = {
     "sat_ppo_actor_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _P]),
     "sat_ppo_critic_grad": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "sat_ppo_adam": (C.c_int, [_P, _P, _F, _F, _F, _F, _F, _P, _P]),
+    "sat_ppo_adam_peers": (C.c_int, [_P, _P, _F, _F, _F, _F, _F, _P, _P, _I32, _I64, _P]),
     "sat_reachable_domain": (C.c_int, [_P, _P, _I64, _I32, _I32, _D, _P, _P, _P, _P]),
     "sat_orbital_elements": (C.c_int, [_P, _I64, _D, _P, _P, _P]),
     "sat_state_from_elements": (C.c_int, [_P, _I64, _D, _P, _P]),

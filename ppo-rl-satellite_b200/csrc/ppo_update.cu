@@ -546,7 +546,8 @@ __device__ __forceinline__ int packed_index(int i, int heads) {
 __global__ void __cluster_dims__(ADAM_CTAS, 1, 1) __launch_bounds__(ADAM_THREADS)
 ppo_adam_kernel(float* __restrict__ params, float* __restrict__ packed, const float* __restrict__ grads,
                 float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int heads, const float* __restrict__ lr_ptr,
-                float beta1, float beta2, float eps, float max_norm, float grad_scale, int64_t* __restrict__ step_ptr) {
+                float beta1, float beta2, float eps, float max_norm, float grad_scale, int64_t* __restrict__ step_ptr,
+                const float* const* __restrict__ peers, int world, int64_t peer_off) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float warp_sums[32];
     __shared__ float cta_sum;
@@ -556,7 +557,17 @@ ppo_adam_kernel(float* __restrict__ params, float* __restrict__ packed, const fl
 #pragma unroll
     for (int k = 0; k < ADAM_PER; ++k) {
         const int i = gtid + k * ADAM_CTAS * ADAM_THREADS;
-        g[k] = i < total ? grads[i] * grad_scale : 0.0f;
+        float gi = 0.0f;
+        if (i < total) {
+            if (peers) {
+                // gradient all-reduce fused into the optimiser step: every rank reads all ranks' flat gradients from
+                // NVLink peer memory (symmetric allocation) and adds them in rank order, so the replicas stay bit-identical
+                for (int r = 0; r < world; ++r) gi += __ldcg(peers[r] + peer_off + i);
+            } else {
+                gi = grads[i];
+            }
+        }
+        g[k] = gi * grad_scale;
         ss = fmaf(g[k], g[k], ss);
     }
 #pragma unroll
@@ -708,7 +719,21 @@ int sat_ppo_adam(const SatPpoNet* net, const float* lr, float beta1, float beta2
     if (!lr || !step) return SAT_ERR_NULL;
     ppo_adam_kernel<<<ADAM_CTAS, ADAM_THREADS, 0, (cudaStream_t)stream>>>(net->params, net->packed, net->grads, net->exp_avg,
                                                                          net->exp_avg_sq, net->heads, lr, beta1, beta2, eps,
-                                                                         max_grad_norm, grad_scale, step);
+                                                                         max_grad_norm, grad_scale, step, nullptr, 1, 0);
+    return launch_status();
+}
+
+int sat_ppo_adam_peers(const SatPpoNet* net, const float* lr, float beta1, float beta2, float eps, float max_grad_norm,
+                       float grad_scale, int64_t* step, const float* const* peer_grads, int world, int64_t offset_floats,
+                       void* stream) {
+    int rc = check_net(net);
+    if (rc) return rc;
+    if (!lr || !step || !peer_grads) return SAT_ERR_NULL;
+    if (world < 1 || world > 64 || offset_floats < 0) return SAT_ERR_SIZE;
+    ppo_adam_kernel<<<ADAM_CTAS, ADAM_THREADS, 0, (cudaStream_t)stream>>>(net->params, net->packed, net->grads, net->exp_avg,
+                                                                         net->exp_avg_sq, net->heads, lr, beta1, beta2, eps,
+                                                                         max_grad_norm, grad_scale, step, peer_grads, world,
+                                                                         offset_floats);
     return launch_status();
 }
 

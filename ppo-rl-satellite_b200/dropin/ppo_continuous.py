@@ -164,6 +164,25 @@ class PPO_continuous:
                 n.bind(_eng.ppo_workspace(mb, self.device))
         return f
 
+    def _peer_allreduce(self, f, group):
+        """True when the gradient all-reduce runs inside the Adam kernel over NVLink peer memory (NCCL process group on
+        CUDA, torch symmetric memory available, SAT_PEER_ALLREDUCE != 0); otherwise the step calls dist.all_reduce."""
+        if "peers" not in f:
+            dist = torch.distributed
+            ok = os.environ.get("SAT_PEER_ALLREDUCE", "1") != "0" and dist.get_backend(group) == "nccl"
+            if ok:
+                try:
+                    for n in f["nets"]:
+                        n.enable_peer_allreduce(group)
+                except Exception as exc:          # no peer access / symmetric memory on this system: NCCL path
+                    import warnings
+                    warnings.warn(f"symmetric-memory gradient exchange unavailable ({exc!r}); using NCCL all-reduce")
+                    ok = False
+                    for n in f["nets"]:
+                        n._peer = None
+            f["peers"] = ok
+        return f["peers"]
+
     def _optimize_fused(self, s, a, a_logprob, adv, v_target, mb, group):
         """The actor chain and the critic chain are independent (ppo_continuous.py:216-239 shares only s[index]), so each
         runs on its own stream: one network's short kernels (partial sums, Adam) hide under the other's GEMM kernels."""
@@ -172,6 +191,9 @@ class PPO_continuous:
         B = s.shape[0]
         f = self._fused_for(min(mb, B))
         na, nc = f["nets"]
+        peers = False
+        if world > 1:
+            peers = self._peer_allreduce(f, group)
         s, a, a_logprob = s.contiguous(), a.contiguous(), a_logprob.contiguous()
         adv, v_target = adv.reshape(-1).contiguous(), v_target.reshape(-1).contiguous()
         clip = 0.5 if self.use_grad_clip else 0.0
@@ -186,12 +208,12 @@ class PPO_continuous:
                 index = perm.data_ptr() + 8 * lo
                 with torch.cuda.stream(sa):
                     na.actor_grad(s, a, a_logprob, adv, index, m, self.epsilon, self.entropy_coef)
-                    if world > 1:
+                    if world > 1 and not peers:
                         dist.all_reduce(na.grads, group=group)
                     na.adam(clip, 1.0 / world)
                 with torch.cuda.stream(sc):
                     nc.critic_grad(s, v_target, index, m)
-                    if world > 1:
+                    if world > 1 and not peers:
                         dist.all_reduce(nc.grads, group=group)
                     nc.adam(clip, 1.0 / world)
         main.wait_stream(sa); main.wait_stream(sc)

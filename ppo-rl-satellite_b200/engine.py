@@ -465,7 +465,29 @@ class PpoFusedNet:
         self.use_tanh, self.max_action = int(bool(use_tanh)), float(max_action)
         self.workspace = None
         self.net = None
+        self._peer = None
         self.adopt()
+
+    # ---- multi-GPU: gradient all-reduce fused into the Adam kernel over NVLink peer memory
+    def enable_peer_allreduce(self, group=None):
+        """Moves the flat gradient into a torch symmetric-memory allocation (two halves, alternated per step) that every
+        rank of `group` maps; `adam()` then orders the ranks with the allocation's device-side barrier and the Adam kernel
+        sums all ranks' gradients itself (sat_ppo_adam_peers) - no NCCL call on the step."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        torch = self.torch
+        g = group if group is not None else dist.group.WORLD
+        stride = _round_up(self.n + 2, 64)
+        buf = symm.empty(2 * stride, dtype=torch.float32, device=self.device)
+        hdl = symm.rendezvous(buf, g.group_name)
+        buf.zero_()
+        self._peer = {"buf": buf, "hdl": hdl, "stride": stride, "parity": 0, "world": int(hdl.world_size),
+                      "ptrs": int(hdl.buffer_ptrs_dev)}
+        self.grads = buf[:self.n + 2]
+        if self.net is not None:
+            self.net.grads = self.grads.data_ptr()
+        hdl.barrier()
+        return self
 
     def _slices(self):
         names = self.CRITIC_NAMES if self.critic else self.ACTOR_NAMES
@@ -519,8 +541,22 @@ class PpoFusedNet:
                 "sat_ppo_critic_grad")
 
     def adam(self, max_grad_norm: float, grad_scale: float = 1.0):
-        L.check(self.lib.sat_ppo_adam(C.byref(self.net), L.ptr(self.lr), self.betas[0], self.betas[1], self.eps,
-                                      float(max_grad_norm), float(grad_scale), L.ptr(self.step), L.stream_ptr()), "sat_ppo_adam")
+        pr = self._peer
+        if pr is None:
+            L.check(self.lib.sat_ppo_adam(C.byref(self.net), L.ptr(self.lr), self.betas[0], self.betas[1], self.eps,
+                                          float(max_grad_norm), float(grad_scale), L.ptr(self.step), L.stream_ptr()), "sat_ppo_adam")
+            return
+        # every rank's gradient kernels for this step are stream-ordered before its barrier; a rank can run at most one
+        # step ahead of the slowest (the next barrier holds it), hence the two alternating halves of the buffer
+        pr["hdl"].barrier()
+        off = pr["parity"] * pr["stride"]
+        L.check(self.lib.sat_ppo_adam_peers(C.byref(self.net), L.ptr(self.lr), self.betas[0], self.betas[1], self.eps,
+                                            float(max_grad_norm), float(grad_scale), L.ptr(self.step), pr["ptrs"], pr["world"],
+                                            off, L.stream_ptr()), "sat_ppo_adam_peers")
+        pr["parity"] ^= 1
+        off = pr["parity"] * pr["stride"]
+        self.grads = pr["buf"][off:off + self.n + 2]
+        self.net.grads = self.grads.data_ptr()
 
     def state_dict(self):
         return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step.clone()}
