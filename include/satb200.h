@@ -118,6 +118,14 @@ int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const in
                  double* obs_stats, double* ret_stats, double* ret_std_out, void* workspace,
                  const SatEnvParams* p, void* stream);
 
+/* Measurement form of sat_env_step (bench.py): the same launches with CUDA events recorded between them on `stream`;
+ * synchronises, then ms_out[0..2] (host) = front (propagation) kernel, finish kernel, statistics merge. In cw mode the
+ * single fused kernel is reported in ms_out[1] and ms_out[0] is ~0. */
+int sat_env_step_timed(const SatEnvState* st, const void* pa, const void* ea, const int32_t* count_override,
+                       float* obs_f32, double* obs_f64, double* term_obs_f64, double* reward, uint8_t* done,
+                       double* obs_stats, double* ret_stats, double* ret_std_out, void* workspace,
+                       const SatEnvParams* p, void* stream, float* ms_out);
+
 /* batched danger-zone count on explicit inertial states. Replaces
  * Time_window_of_danger_zone(R0_c, V0_c, R0_t, V0_t, Delta_V_c).calculate_number_of_hanger_area()
  * (satellite_function.py:18-99, 341-373). rv [n][12] = R0_c, V0_c, R0_t, V0_t; dv [n] = Delta_V_c.

@@ -700,10 +700,14 @@ int sat_env_observe(const SatEnvState* st, float* obs_f32, double* obs_f64, void
     return launch_status();
 }
 
-int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const int32_t* count_override,
-                 float* obs_f32, double* obs_f64, double* term_obs_f64, double* reward, uint8_t* done,
-                 double* obs_stats, double* ret_stats, double* ret_std_out, void* workspace,
-                 const SatEnvParams* p, void* stream) {
+}  // extern "C"
+
+namespace {
+// ev (nullable): 4 events recorded before the first launch and after the front / finish / merge launches
+int env_step_impl(const SatEnvState* st, const void* pa, const void* ea, const int32_t* count_override,
+                  float* obs_f32, double* obs_f64, double* term_obs_f64, double* reward, uint8_t* done,
+                  double* obs_stats, double* ret_stats, double* ret_std_out, void* workspace,
+                  const SatEnvParams* p, void* stream, cudaEvent_t* ev) {
     int rc = check_state(st);
     if (rc) return rc;
     if (!pa || !ea || !reward || !done || !p) return SAT_ERR_NULL;
@@ -721,8 +725,10 @@ int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const in
     unsigned int* ticket = ws ? (unsigned int*)ws : nullptr;
     double* dis_prev = ws ? (double*)(ws + ws_disprev_offset()) : nullptr;
     double* partials = want_stats ? (double*)(ws + ws_partials_offset(n)) : nullptr;
+    if (ev) cudaEventRecord(ev[0], s);
     if (p->mode == SAT_MODE_CW) {
         // one fused kernel: the propagation is a 6x6 product
+        if (ev) cudaEventRecord(ev[1], s);
         if (p->action_dtype == SAT_ACT_F32)
             env_step_kernel<true, float, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, nullptr, partials, ticket, *p);
@@ -734,21 +740,57 @@ int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const in
         const int64_t fblocks = (2 * n + kFrontBlock - 1) / kFrontBlock;
         if (p->action_dtype == SAT_ACT_F32) {
             env_front_rk4_kernel<float><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea, dis_prev, *p);
+            if (ev) cudaEventRecord(ev[1], s);
             env_step_kernel<false, float, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
         } else {
             env_front_rk4_kernel<double><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea, dis_prev, *p);
+            if (ev) cudaEventRecord(ev[1], s);
             env_step_kernel<false, double, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
         }
     }
     rc = launch_status();
     if (rc) return rc;
+    if (ev) cudaEventRecord(ev[2], s);
     if (partials) {
         stats_merge_kernel<<<kStatDims, kMergeThreads, 0, s>>>(partials, nblocks, n, kEnvsPerBlock, kStatDims,
                                                                obs_stats, kObs, ret_stats, ret_std_out, ticket);
         rc = launch_status();
     }
+    if (ev) cudaEventRecord(ev[3], s);
+    return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int sat_env_step(const SatEnvState* st, const void* pa, const void* ea, const int32_t* count_override,
+                 float* obs_f32, double* obs_f64, double* term_obs_f64, double* reward, uint8_t* done,
+                 double* obs_stats, double* ret_stats, double* ret_std_out, void* workspace,
+                 const SatEnvParams* p, void* stream) {
+    return env_step_impl(st, pa, ea, count_override, obs_f32, obs_f64, term_obs_f64, reward, done, obs_stats, ret_stats,
+                         ret_std_out, workspace, p, stream, nullptr);
+}
+
+int sat_env_step_timed(const SatEnvState* st, const void* pa, const void* ea, const int32_t* count_override,
+                       float* obs_f32, double* obs_f64, double* term_obs_f64, double* reward, uint8_t* done,
+                       double* obs_stats, double* ret_stats, double* ret_std_out, void* workspace,
+                       const SatEnvParams* p, void* stream, float* ms_out) {
+    if (!ms_out) return SAT_ERR_NULL;
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; ++i) {
+        cudaError_t ce = cudaEventCreate(&ev[i]);
+        if (ce != cudaSuccess) return (int)ce;
+    }
+    int rc = env_step_impl(st, pa, ea, count_override, obs_f32, obs_f64, term_obs_f64, reward, done, obs_stats, ret_stats,
+                           ret_std_out, workspace, p, stream, ev);
+    if (rc == SAT_OK) {
+        cudaError_t ce = cudaEventSynchronize(ev[3]);
+        if (ce != cudaSuccess) rc = (int)ce;
+        else for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
     return rc;
 }
 

@@ -223,6 +223,21 @@ class EnvBatch:
                                       L.stream_ptr()), "sat_env_step")
         return reward, done
 
+    def step_timed(self, pa, ea, reward=None, done=None, obs_stats: RunningStats | None = None,
+                   ret_stats: RunningStats | None = None):
+        """step() through sat_env_step_timed: returns (front_ms, finish_ms, merge_ms) measured with CUDA events recorded
+        between the launches on the launching stream (bench.py's per-kernel roofline)."""
+        self.params.action_dtype = L.ACT_F32 if pa.dtype == self.torch.float32 else L.ACT_F64
+        ms = (C.c_float * 3)()
+        L.check(self.lib.sat_env_step_timed(C.byref(self.st), L.ptr(pa), L.ptr(ea), None, None, None, None,
+                                            L.ptr(self.reward if reward is None else reward),
+                                            L.ptr(self.done if done is None else done),
+                                            L.ptr(obs_stats.buf) if obs_stats is not None else None,
+                                            L.ptr(ret_stats.buf) if ret_stats is not None else None, None,
+                                            self.workspace.data_ptr(), C.byref(self.params), L.stream_ptr(), ms),
+                "sat_env_step_timed")
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
     # -- host-buffer form: the reference-facing call with numpy in / numpy out (e2e path)
     def host_buffers(self):
         """pinned host arrays (pa, ea, obs, reward, done). Filling pa/ea in place and passing them to step_host()
