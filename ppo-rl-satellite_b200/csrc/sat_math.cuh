@@ -193,6 +193,11 @@ struct PFai {
 template <class F>
 struct Hybrd1 {
     F f;
+    // a / b for a >= +0, b > 0 (b may be NaN): identical bits to the plain quotient, but a == 0 never reaches the divider
+    static SAT_DEV double zdiv(double a, double b) {
+        const double q = ((a == 0.0) ? 1.0 : a) / b;
+        return (a == 0.0 && b == b) ? 0.0 : q;
+    }
     double x, fv, fnorm, d, delta, xnorm, r, q, qtf, h, xt, p, pnorm;
     int nfev, iter, ncsuc, ncfail, nslow1, nslow2, phase;   // phase 0: f(x0), 1: f(x+h) (Jacobian), 2: f(xt) (trial)
     bool jeval;
@@ -260,15 +265,19 @@ struct Hybrd1 {
         } else {
             const double ft = fe;
             const double fnorm1 = fabs(ft);
-            const double actred = (fnorm1 < fnorm) ? 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm) : -1.0;
+            // zdiv: a zero numerator (exact root; exactly-zero predicted residual of the 1-D Newton step, i.e. nearly every
+            // iteration) would take the whole warp through the division's zero/denormal slow path; 0 / b is +0 here
+            const double qa = zdiv(fnorm1, fnorm);
+            const double actred = (fnorm1 < fnorm) ? 1.0 - qa * qa : -1.0;
             const double pred = qtf + r * p;
-            const double prered = (fabs(pred) < fnorm) ? 1.0 - (fabs(pred) / fnorm) * (fabs(pred) / fnorm) : 0.0;
+            const double qp = zdiv(fabs(pred), fnorm);
+            const double prered = (fabs(pred) < fnorm) ? 1.0 - qp * qp : 0.0;
             const double ratio = (prered > 0.0) ? actred / prered : 0.0;
             if (ratio < 0.1) { ncsuc = 0; ++ncfail; delta = 0.5 * delta; }
             else {
                 ncfail = 0; ++ncsuc;
-                if (ratio >= 0.5 || ncsuc > 1) delta = fmax(delta, pnorm / 0.5);
-                if (fabs(ratio - 1.0) <= 0.1) delta = pnorm / 0.5;
+                if (ratio >= 0.5 || ncsuc > 1) delta = fmax(delta, pnorm * 2.0);      // pnorm / 0.5 (MINPACK: pnorm/p5), exact
+                if (fabs(ratio - 1.0) <= 0.1) delta = pnorm * 2.0;
             }
             if (ratio >= 1e-4) { x = xt; fv = ft; xnorm = fabs(d * x); fnorm = fnorm1; ++iter; }
             ++nslow1; if (actred >= 1e-3) nslow1 = 0;
@@ -364,10 +373,20 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     sincos(df, &sdf, &cdf);
     const double tmp1 = (sdf * sdf) / (u_grav * (k * k) / (p_c * (dv * dv)) - 1.0);   // :466 / :481
     if (!(0.0 <= tmp1)) { nd.status = 1; return; }                                    // :478 -> (0, 0)
-    const double beta = atan(0.0 / sdf);                                              // :469, tan(fai) = 0
-    double sb, cb;
-    sincos(beta, &sb, &cb);
-    const double dvm = sqrt(dv * dv - u_grav * (k * k) * (sb * sb) / p_c);            // :470
+    // :469-470 with tan(fai) = 0: beta = atan(+-0 / sdf) = +-0 for every finite non-zero sdf, so cos(beta) = 1 and the
+    // subtracted term u k^2 sin(beta)^2 / p_c is +-0 (u k^2 finite, p_c non-zero): dvm = sqrt(dv^2) bit for bit. The general
+    // form stays for the other inputs; the shortcut keeps a zero-numerator division (warp-wide slow path), an atan and a
+    // sincos off the common path.
+    double cb, dvm;
+    if (sdf != 0.0 && fabs(sdf) <= 1.0 && fabs(u_grav * (k * k)) <= 1.7976931348623157e308 && p_c != 0.0 && p_c == p_c) {
+        cb = 1.0;
+        dvm = sqrt(dv * dv);
+    } else {
+        const double beta = atan(0.0 / sdf);                                          // :469
+        double sb;
+        sincos(beta, &sb, &cb);
+        dvm = sqrt(dv * dv - u_grav * (k * k) * (sb * sb) / p_c);                     // :470
+    }
     double theta = 0.0;                                                               // :464 (stays 0 outside both ranges, Q5)
     if ((-kTwoPi <= df && df < -kPi) || (0.0 <= df && df < kPi)) theta = acos(cdf * 1.0);             // :473-474
     else if ((-kPi <= df && df < 0.0) || (kPi <= df && df < kTwoPi)) theta = kTwoPi - acos(cdf * 1.0);  // :475-476
@@ -385,7 +404,13 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
         const double v1x = sq_e_sin + dvm * cg;
         const double v1y = sq_k + dvm * sg;
         const double h = r_c * v1y;                                                   // :521
-        const double A = (2.0 * u_grav * (1.0 - cth)) / (h * v1y) - v1x * sth / v1y;  // :560
+        // :560. theta == 0 (45 % of the nodes the env visits) gives (+0) / (h v1y) - (+-0) / v1y = +-0 when the
+        // denominators are non-zero numbers and v1x is finite; the sign of that zero is never observed (dz_degenerate),
+        // and skipping the two zero-numerator divisions keeps the warp off the division slow path
+        const double hv = h * v1y;
+        double A;
+        if (sth == 0.0 && cth == 1.0 && hv != 0.0 && hv == hv && v1y != 0.0 && fabs(v1x) <= 1.7976931348623157e308) A = 0.0;
+        else A = (2.0 * u_grav * (1.0 - cth)) / hv - v1x * sth / v1y;
         if (j == 0) nd.A0 = A; else nd.A1 = A;
     }
     nd.status = 2;
