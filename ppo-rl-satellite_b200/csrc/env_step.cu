@@ -178,10 +178,17 @@ SAT_DEV void queue_push(SolveQueue& q, const DzNode& nd, int& slot0, int& slot1,
 
 // persistent lanes: every lane pulls the next root problem as soon as it finishes one, and all lanes of a warp
 // advance their own solver by one function evaluation per loop trip (uniform loop body, no per-task divergence)
+#ifndef SAT_SOLVE_WARPS
+#define SAT_SOLVE_WARPS 4
+#endif
 SAT_DEV void queue_run(SolveQueue& q) {
     const int total = q.count;
     int task = -1;
     Hybrd1<PFai> hs;
+    // root problems take 5..15 evaluations (mean 8), so a warp runs as long as its slowest lane (12.8 trips measured).
+    // Restricting the solve to fewer warps evens the lanes out but lengthens the CTA's serial chain; the kernel is
+    // latency-bound, so all four warps is fastest (env step 174 / 176 / 181 / 209 us with 4 / 3 / 2 / 1 solver warps).
+    if ((threadIdx.x >> 5) < SAT_SOLVE_WARPS)
     for (;;) {
         if (task < 0) {
             const int t = atomicAdd(&q.next, 1);
