@@ -634,3 +634,19 @@ def test_reachable_domain_sweep_vs_reference_and_oracle(golden, oracle, eng):
         assert np.array_equal(v2, ov)
         np.testing.assert_allclose(h2.cpu().numpy()[0][v2], oh, rtol=1e-9, atol=1e-3)
         np.testing.assert_allclose(l2.cpu().numpy()[0][v2], ol, rtol=1e-9, atol=1e-3)
+
+
+def test_step_timed_is_the_same_step(eng):
+    """sat_env_step_timed (bench.py's per-launch timing) runs exactly the launches of sat_env_step"""
+    n = 1000
+    rng = np.random.default_rng(5)
+    kw = dict(mode="rk4", substeps=10, h=1.0, d_capture=20000.0, max_episode_steps=50)
+    a, b = eng.EnvBatch(n, **kw), eng.EnvBatch(n, **kw)
+    for t in range(3):
+        pa = torch.from_numpy(rng.uniform(-2, 2, (n, 3)).astype(np.float32)).cuda()
+        ea = torch.from_numpy(rng.uniform(-2, 2, (n, 3)).astype(np.float32)).cuda()
+        ra, da = a.step(pa, ea)
+        ms = b.step_timed(pa, ea)
+        assert len(ms) == 3 and ms[0] > 0 and ms[1] > 0
+        assert torch.equal(ra, b.reward) and torch.equal(da, b.done)
+    assert torch.equal(a.state, b.state) and torch.equal(a.istate, b.istate)
