@@ -59,7 +59,8 @@ struct Lane {
 
 template <typename ActT>
 SAT_DEV void load_and_gate(const SatEnvState& st, const SatEnvParams& p, const ActT* __restrict__ pa,
-                           const ActT* __restrict__ ea, int64_t e, int craft, Lane& L, bool do_impulse) {
+                           const ActT* __restrict__ ea, int64_t e, int craft, Lane& L, bool do_impulse,
+                           const ActT* raw = nullptr /* the lane's action already in registers */) {
     const int64_t ld = st.ld;
     const double* __restrict__ S = st.state;
     const int32_t* __restrict__ I = st.istate;
@@ -73,7 +74,7 @@ SAT_DEV void load_and_gate(const SatEnvState& st, const SatEnvParams& p, const A
     {
         const ActT* act = craft ? ea : pa;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) L.a[k] = clip16((double)act[e * 3 + k]);
+        for (int k = 0; k < 3; ++k) L.a[k] = clip16((double)(raw ? raw[k] : act[e * 3 + k]));
     }
     bool frozen;                                            // gating uses LAST step's dis / dangerous_zone (Q3)
     if (p.flag == 0) frozen = (craft == 0) && (dis_stale < p.d_range) && (dz_stale != 0);   // :91-96
@@ -123,17 +124,37 @@ SAT_DEV void propagate_rk4(const SatEnvParams& p, Lane& L) {
 
 // rk4 mode, kernel A: impulse + S RK4 substeps, state written back; |P-E| before the step goes to the workspace.
 // 64-thread CTAs at <= 72 registers: all 2048 CTAs of the 65 536-env batch are resident at once (14 per SM).
-template <typename ActT>
+// OBS = true (host-buffer path): the kernel also writes the step's NEXT observation (after the auto reset) to obs_early.
+// The observation depends only on the propagated state and the terminal checks, not on the danger-zone solve of kernel
+// B, so its device-to-host copy can run on a copy engine underneath kernel B.
+template <typename ActT, bool OBS>
 __global__ void __launch_bounds__(kFrontBlock, 14)
 env_front_rk4_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* __restrict__ ea,
-                     double* __restrict__ dis_prev_out, const __grid_constant__ SatEnvParams p) {
+                     double* __restrict__ dis_prev_out, float* __restrict__ obs_early,
+                     float* __restrict__ pa_copy, float* __restrict__ ea_copy, const __grid_constant__ SatEnvParams p) {
     const int64_t tid = (int64_t)blockIdx.x * kFrontBlock + threadIdx.x;
     const int64_t env_raw = tid >> 1;
     const int craft = (int)(tid & 1);
     const bool valid = env_raw < st.n;
     const int64_t e = valid ? env_raw : st.n - 1;
     Lane L;
-    load_and_gate(st, p, pa, ea, e, craft, L, true);
+    if (OBS) {
+        // host-buffer path: pa / ea live in host memory. Each action is read over PCIe exactly once, here, and left in
+        // device memory for kernel B - whose reads would otherwise queue behind the observation copy's posted writes
+        // (PCIe ordering: a read request may not pass a write in the same direction)
+        ActT raw[3];
+        const ActT* act = craft ? ea : pa;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) raw[k] = act[e * 3 + k];
+        if (valid) {
+            float* dc = craft ? ea_copy : pa_copy;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dc[e * 3 + k] = (float)raw[k];
+        }
+        load_and_gate(st, p, pa, ea, e, craft, L, true, raw);
+    } else {
+        load_and_gate(st, p, pa, ea, e, craft, L, true);
+    }
     propagate_rk4(p, L);
     if (valid) {
         const int64_t ld = st.ld;
@@ -142,6 +163,34 @@ env_front_rk4_kernel(const SatEnvState st, const ActT* __restrict__ pa, const Ac
         for (int k = 0; k < 3; ++k) { st.state[(base + k) * ld + e] = L.r[k]; st.state[(base + 3 + k) * ld + e] = L.v[k]; }
         st.state[(SAT_COL_FUEL_C + craft) * ld + e] = L.fuel_own;
         if (craft == 0) dis_prev_out[e] = L.dis_prev;
+    }
+    if (OBS) {
+        // same arithmetic as kernel B: exchange, |P - E|, terminal checks (environment.py:130-147), reset values (:66-79)
+        double P[3], Pv[3], E[3], Ev[3], d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double o_r = shfl1(L.r[k]), o_v = shfl1(L.v[k]);
+            P[k] = craft == 0 ? L.r[k] : o_r;  Pv[k] = craft == 0 ? L.v[k] : o_v;
+            E[k] = craft == 0 ? o_r : L.r[k];  Ev[k] = craft == 0 ? o_v : L.v[k];
+            d[k] = __dsub_rn(P[k], E[k]);
+        }
+        const double dis = norm3(d);
+        const int count_new = st.istate[SAT_ICOL_COUNT * st.ld + e] + 1;
+        const bool done = (dis <= p.d_capture) || (count_new >= p.max_episode_steps);
+        if (done && p.auto_reset) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { P[k] = p.reset_p[k]; E[k] = p.reset_e[k]; Pv[k] = 0.0; Ev[k] = 0.0; }
+        }
+        if (valid) {
+            float* o = obs_early + e * kObs + craft * 9;
+            if (craft == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { o[k] = (float)__dsub_rn(P[k], E[k]); o[3 + k] = (float)__dsub_rn(Pv[k], Ev[k]); o[6 + k] = (float)P[k]; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { o[k] = (float)Pv[k]; o[3 + k] = (float)E[k]; o[6 + k] = (float)Ev[k]; }
+            }
+        }
     }
 }
 
@@ -714,7 +763,8 @@ namespace {
 int env_step_impl(const SatEnvState* st, const void* pa, const void* ea, const int32_t* count_override,
                   float* obs_f32, double* obs_f64, double* term_obs_f64, double* reward, uint8_t* done,
                   double* obs_stats, double* ret_stats, double* ret_std_out, void* workspace,
-                  const SatEnvParams* p, void* stream, cudaEvent_t* ev) {
+                  const SatEnvParams* p, void* stream, cudaEvent_t* ev, float* obs_early = nullptr,
+                  cudaEvent_t front_done = nullptr, float* pa_copy = nullptr, float* ea_copy = nullptr) {
     int rc = check_state(st);
     if (rc) return rc;
     if (!pa || !ea || !reward || !done || !p) return SAT_ERR_NULL;
@@ -745,13 +795,20 @@ int env_step_impl(const SatEnvState* st, const void* pa, const void* ea, const i
     } else {
         // kernel A (FP64-pipe bound, <= 72 registers, whole batch resident) then kernel B (register-heavy, divergent)
         const int64_t fblocks = (2 * n + kFrontBlock - 1) / kFrontBlock;
-        if (p->action_dtype == SAT_ACT_F32) {
-            env_front_rk4_kernel<float><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea, dis_prev, *p);
+        if (obs_early && (count_override || p->action_dtype != SAT_ACT_F32 || !pa_copy || !ea_copy)) return SAT_ERR_MODE;
+        if (obs_early) {
+            env_front_rk4_kernel<float, true><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
+                                                                                       dis_prev, obs_early, pa_copy, ea_copy, *p);
+            if (front_done) cudaEventRecord(front_done, s);
+            env_step_kernel<false, float, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, pa_copy, ea_copy,
+                count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
+        } else if (p->action_dtype == SAT_ACT_F32) {
+            env_front_rk4_kernel<float, false><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea, dis_prev, nullptr, nullptr, nullptr, *p);
             if (ev) cudaEventRecord(ev[1], s);
             env_step_kernel<false, float, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
         } else {
-            env_front_rk4_kernel<double><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea, dis_prev, *p);
+            env_front_rk4_kernel<double, false><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea, dis_prev, nullptr, nullptr, nullptr, *p);
             if (ev) cudaEventRecord(ev[1], s);
             env_step_kernel<false, double, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
@@ -837,11 +894,10 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
     SatEnvParams q = *p;
     q.action_dtype = SAT_ACT_F32;
     if (chunks <= 0) {
-        // zero-copy form: pinned (UVA-mapped) host buffers are handed to the kernels directly. The finish kernel's
-        // coalesced observation/reward/done stores stream to host memory over PCIe while other CTAs still compute, and
-        // the 12-byte action reads hide behind the RK4 work, so no separate copy phase remains. With chunks < 0 the batch
-        // is additionally cut into -chunks env ranges alternating between the two streams.
-        // (measured at 65 536 envs: zero-copy 283 us/step; DMA inputs + zero-copy outputs 296; staged copies 327)
+        // zero-copy form: pinned (UVA-mapped) host buffers are handed to the kernels directly: the action reads and the
+        // observation / reward / done stores cross PCIe from inside the kernels. With chunks < 0 the batch is additionally
+        // cut into -chunks env ranges alternating between the two streams. In rk4 mode with one range (chunks == 0) the
+        // observation instead leaves through a copy engine underneath kernel B (below).
         cudaPointerAttributes at;
         bool ok = true;
         const void* ptrs[5] = {pa_host, ea_host, obs_host, reward_host, done_host};
@@ -853,6 +909,28 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
         cudaGetLastError();
         int ranges = (chunks < 0 && s1) ? -chunks : 1;
         if (ranges > 16) ranges = 16;
+        if (ok && ranges == 1 && s1 && q.mode == SAT_MODE_RK4) {
+            // rk4 mode, one range (the default): kernel A reads the actions from host memory (zero-copy), leaves a copy in
+            // device memory for kernel B and writes the step's next observation (88 % of the output bytes) to device
+            // memory; a copy engine moves the observation to the host on the second stream while kernel B (danger zone,
+            // reward) runs; kernel B writes reward / done straight to host memory. Kernel B must not READ host memory
+            // here: PCIe read requests may not pass the copy's posted writes, which stalled it by ~50 us.
+            // Measured at 65 536 envs: 241 us/step (all zero-copy: 287; two zero-copy ranges: 266; staged: 306).
+            static thread_local cudaEvent_t front_ev[16] = {};
+            int devid = 0;
+            cudaGetDevice(&devid);
+            cudaEvent_t& fe = front_ev[devid & 15];
+            cudaError_t ce0;
+            if (!fe && (ce0 = cudaEventCreateWithFlags(&fe, cudaEventDisableTiming)) != cudaSuccess) return (int)ce0;
+            rc = env_step_impl(st, dev[0], dev[1], nullptr, nullptr, nullptr, nullptr, (double*)dev[3], (uint8_t*)dev[4],
+                               nullptr, nullptr, nullptr, d_ws, &q, (void*)s0, nullptr, d_obs, fe, d_pa, d_ea);
+            if (rc) return rc;
+            if ((ce0 = cudaStreamWaitEvent(s1, fe, 0)) != cudaSuccess) return (int)ce0;
+            if ((ce0 = cudaMemcpyAsync(obs_host, d_obs, (size_t)n * 72, cudaMemcpyDeviceToHost, s1)) != cudaSuccess) return (int)ce0;
+            if ((ce0 = cudaStreamSynchronize(s0)) != cudaSuccess) return (int)ce0;
+            if ((ce0 = cudaStreamSynchronize(s1)) != cudaSuccess) return (int)ce0;
+            return SAT_OK;
+        }
         if (ok) {
             const int64_t per = ((n + ranges - 1) / ranges + 63) / 64 * 64;
             const int64_t ws_per = sat_workspace_bytes(per);

@@ -226,6 +226,30 @@ def test_env_step_host_buffers(golden, oracle, eng):
         assert np.array_equal(d, o_d) and np.array_equal(r, o_r) and np.array_equal(obs, o_obs.astype(np.float32))
 
 
+def test_env_step_host_rk4_forms_equal_device_step(eng):
+    """rk4 mode: every host-buffer form (overlapped observation copy = default, zero-copy ranges, staged) returns exactly
+    what the device-resident step returns, including the observation after an auto reset (captures and time-outs occur)"""
+    n = 1500
+    rng = np.random.default_rng(11)
+    kw = dict(mode="rk4", substeps=5, h=1.0, d_capture=150000.0, max_episode_steps=6)
+    for chunks in (0, -2, -3, 1, 2):
+        a, b = eng.EnvBatch(n, **kw), eng.EnvBatch(n, **kw)
+        P0 = np.array([200000.0, 0, 0]) + rng.normal(0, 6e4, (n, 3)); E0 = np.array([18000.0, 0, 0]) + rng.normal(0, 6e4, (n, 3))
+        V0 = rng.normal(0, 3.0, (n, 3)); W0 = rng.normal(0, 3.0, (n, 3))
+        a.set_state(P0, V0, E0, W0); b.set_state(P0, V0, E0, W0)
+        obs_d = torch.empty((n, 18), dtype=torch.float32, device="cuda")
+        dones = 0
+        for t in range(9):
+            pa = rng.uniform(-2, 2, (n, 3)).astype(np.float32); ea = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+            r, d = a.step(torch.from_numpy(pa).cuda(), torch.from_numpy(ea).cuda(), obs_f32=obs_d)
+            obs, rh, dh = b.step_host(pa, ea, chunks=chunks)
+            assert np.array_equal(dh, d.cpu().numpy()) and np.array_equal(rh, r.cpu().numpy())
+            assert np.array_equal(obs, obs_d.cpu().numpy())
+            dones += int(dh.sum())
+        assert dones > n                                       # every env timed out at least once, some were captured
+        assert torch.equal(a.state, b.state) and torch.equal(a.istate, b.istate)
+
+
 def test_env_argument_errors(eng):
     from ppo_rl_satellite_b200 import _lib as L
     import ctypes as C

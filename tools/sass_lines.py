@@ -21,6 +21,8 @@ data = []
 for r in rows[2:]:
     try: data.append((int(r[si]), int(r[ii]), r[1], int(r[ti])))
     except Exception: pass
+if len(data) > len(instr) and len(data) % len(instr) == 0:
+    data = data[:len(instr)]          # the csv lists every matching launch back to back: keep the first
 assert len(instr) == len(data), (len(instr), len(data))
 agg = collections.defaultdict(lambda: [0, 0, 0])
 for (c, _), d in zip(instr, data):
