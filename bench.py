@@ -401,8 +401,9 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": n * world * ke / float(dt.item()), "unit": "env-steps/s",
                "h2d_bytes_per_step": env.h2d_bytes_per_step, "d2h_bytes_per_step": env.d2h_bytes_per_step,
                "api": "EnvBatch.step_host(pa, ea) -> (obs, reward, done) = one sat_env_step_host call on pinned host arrays: the "
-                      "kernels read the actions from and write obs/reward/done to host memory directly (UVA zero-copy over PCIe, "
-                      "overlapped with compute; two env ranges on two streams), then the streams are synchronised; wall clock",
+                      "propagation kernel reads the actions from host memory (zero-copy) and emits the next observation, a copy engine "
+                      "moves it to the host on a second stream while the danger-zone kernel runs, reward/done are written to host "
+                      "memory by that kernel; both streams are synchronised before the call returns; wall clock",
                "steps": ke}
     # ---------------- PPO samples/sec (BASELINE config 5 shape, per-GPU share): rollout + GAE + K-epoch update
     ppo = None
