@@ -1,5 +1,5 @@
 // mlp_tile.cuh -- shared pieces of the fp32 MLP kernels (actor.cu: forward + sampling; ppo_update.cu: forward/backward):
-// the packed weight image, TMA bulk-copy / mbarrier wrappers, the fast tanh and the 8 x 16 FFMA2 register tile.
+// the packed weight image, TMA bulk-copy / mbarrier wrappers, the fast tanh and the 8 x CT FFMA2 register tile.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

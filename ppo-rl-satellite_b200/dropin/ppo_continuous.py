@@ -91,7 +91,7 @@ class Critic(nn.Module):
 def allreduce_grads_(module, group=None):
     """Average gradients across ranks with ONE flat all-reduce per network (286 KB actor / 284 KB critic)."""
     dist = torch.distributed
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    if group is False or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     grads = [p.grad for p in module.parameters() if p.grad is not None]
     flat = torch.cat([g.reshape(-1) for g in grads])
@@ -187,7 +187,10 @@ class PPO_continuous:
         """The actor chain and the critic chain are independent (ppo_continuous.py:216-239 shares only s[index]), so each
         runs on its own stream: one network's short kernels (partial sums, Adam) hide under the other's GEMM kernels."""
         dist = torch.distributed
-        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if group is False:                            # explicit "no gradient exchange" (single-rank use inside a job)
+            world, group = 1, None
+        else:
+            world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         B = s.shape[0]
         f = self._fused_for(min(mb, B))
         na, nc = f["nets"]
