@@ -33,7 +33,10 @@ constexpr int kFrontBlock = 64;         // rk4 front (impulse + propagation) ker
 // kernel B is latency bound (long dependent FP64 chains: divisions, sqrt, acos, sincos): measured on B200 at 65 536
 // envs, total env-step time vs min-blocks-per-SM {1: 250, 4: 200, 7: 185, 8: 187, 10: 201, 12: 231} us. 7 CTAs x 128
 // threads at 72 registers (some spills to L1) beats 186 registers at 2 CTAs.
-constexpr int kFinishMinBlocks = 7;
+#ifndef SAT_FINISH_MINB
+#define SAT_FINISH_MINB 7
+#endif
+constexpr int kFinishMinBlocks = SAT_FINISH_MINB;
 constexpr int kObs = 18;
 constexpr int kStatDims = 19;           // 18 observation dims + discounted return
 constexpr int kWsHeader = 256;          // workspace: [ticket counter | pad] [dis_prev: n doubles] [partials]
