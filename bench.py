@@ -222,12 +222,32 @@ def run_ppo_section(args, rank, world, dev, torch, dist, eng):
             "timing": "wall clock with barrier + synchronize on both sides, max over ranks"}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: pin this rank (and therefore its first-touch pinned host buffers) to the CPUs NVML reports as local
+    to its GPU, so the e2e path's PCIe traffic does not cross the socket interconnect. Returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus and len(cpus) < os.cpu_count():
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from ppo_rl_satellite_b200 import engine as eng
     from ppo_rl_satellite_b200 import _lib as L
 
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("SAT_NUMA_BIND", "1") != "0" else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     n = args.envs
@@ -404,7 +424,7 @@ def run_ours(args, rank, world, local_rank):
                       "propagation kernel reads the actions from host memory (zero-copy) and emits the next observation, a copy engine "
                       "moves it to the host on a second stream while the danger-zone kernel runs, reward/done are written to host "
                       "memory by that kernel; both streams are synchronised before the call returns; wall clock",
-               "steps": ke}
+               "steps": ke, "rank_cpu_affinity": numa_cpus}
     # ---------------- PPO samples/sec (BASELINE config 5 shape, per-GPU share): rollout + GAE + K-epoch update
     ppo = None
     if not args.no_ppo:
