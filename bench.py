@@ -45,7 +45,7 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3, help="untimed warm-up steps (at least 3 are always run)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--substeps", type=int, default=100)
@@ -58,7 +58,10 @@ def parse():
     ap.add_argument("--ppo-update", choices=("fused", "torch"), default="fused",
                     help="optimiser step: hand-written forward/backward/Adam kernels, or the PyTorch step (CUDA-graphed)")
     ap.add_argument("--cpu-sample-envs", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.warmup_requested = args.warmup
+    args.warmup = max(3, args.warmup)            # timing rule: never fewer than 3 untimed warm-up steps
+    return args
 
 
 # ------------------------------------------------------------------------------------------------ clocks
