@@ -378,16 +378,19 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     if (captured) reward = (p.flag == 0) ? 100.0 : -150.0;
     else if (timeout) reward = (p.flag == 0) ? 0.0 : 100.0;
     else {
-        // the four cosines are split over the lane pair (2 each) and swapped: same values, half the latency
-        double ca, cb;
-        if (craft == 0) {
-            ca = cosine3(P, E);                                                               // pv1 :166
-            cb = cosine3(Pv, Ev);                                                             // pv2 :167
-        } else {
-            ca = cosine3(d, Pv);                                                              // pv3 :168
-            cb = 0.0;                                                                         // pv4 :169
-            if (pa_gated[0] != 0.0 && pa_gated[1] != 0.0 && pa_gated[2] != 0.0) cb = -cosine3(d, pa_gated);
+        // the four cosines are split over the lane pair (2 each) and swapped: same values, half the latency. The operands
+        // are SELECTED per lane and both lanes run the same two cosine3 calls - a branch on `craft` would make every warp
+        // execute all four with half its lanes masked.
+        const bool pv4_on = pa_gated[0] != 0.0 && pa_gated[1] != 0.0 && pa_gated[2] != 0.0;       // :169, else pv4 = 0
+        double u1[3], w1[3], u2[3], w2[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            u1[k] = craft == 0 ? P[k] : d[k];   w1[k] = craft == 0 ? E[k] : Pv[k];               // pv1 :166 | pv3 :168
+            u2[k] = craft == 0 ? Pv[k] : d[k];  w2[k] = craft == 0 ? Ev[k] : (pv4_on ? pa_gated[k] : Pv[k]);   // pv2 :167 | pv4 :169
         }
+        const double ca = cosine3(u1, w1);
+        double cb = cosine3(u2, w2);
+        if (craft == 1) cb = pv4_on ? -cb : 0.0;
         cos_a = ca; cos_b = cb;
     }
     // (warp-convergent point: the swaps below are executed by every lane)
