@@ -387,9 +387,12 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
         sincos(beta, &sb, &cb);
         dvm = sqrt(dv * dv - u_grav * (k * k) * (sb * sb) / p_c);                     // :470
     }
-    double theta = 0.0;                                                               // :464 (stays 0 outside both ranges, Q5)
-    if ((-kTwoPi <= df && df < -kPi) || (0.0 <= df && df < kPi)) theta = acos(cdf * 1.0);             // :473-474
-    else if ((-kPi <= df && df < 0.0) || (kPi <= df && df < kTwoPi)) theta = kTwoPi - acos(cdf * 1.0);  // :475-476
+    // :464, :473-476 (theta stays 0 outside both ranges, Q5). One acos for the warp, the range decides how it is used:
+    // an if / else-if around two acos calls made every warp run the routine twice with part of its lanes.
+    const double ac = acos(cdf * 1.0);
+    const bool in_a = (-kTwoPi <= df && df < -kPi) || (0.0 <= df && df < kPi);
+    const bool in_b = (-kPi <= df && df < 0.0) || (kPi <= df && df < kTwoPi);
+    const double theta = in_a ? ac : (in_b ? kTwoPi - ac : 0.0);
     double sth, cth;
     sincos(theta, &sth, &cth);
     const double sq = sqrt(u_grav / p_c);
