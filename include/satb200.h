@@ -191,6 +191,14 @@ int sat_actor_sample(const SatActorWeights* w, const float* obs_f32, const SatEn
 /* Critic forward (ppo_continuous.py:123-128): v [n] = fc3(tanh(fc2(tanh(fc1(s))))).
  * w3/b3 are fc3.weight [1][hidden] / fc3.bias [1]; log_std unused. */
 int sat_critic_forward(const SatActorWeights* w, const float* obs_f32, int64_t n, float* v, void* stream);
+/* Two Gaussian actors on the same observations in ONE launch (pursuer and evader of a rollout step, CPPO_main.py:122-123):
+ * exactly the results of two sat_actor_sample calls with steps step_a / step_b; obs_out (nullable) receives the fp32
+ * observation once. At small shard sizes both networks then share the GPU instead of running one after the other. */
+int sat_actor_sample_pair(const SatActorWeights* wa, const SatActorWeights* wb, const float* obs_f32, const SatEnvState* st,
+                          const double* obs_stats, int64_t n, int64_t row_offset, uint64_t seed, uint64_t step_a,
+                          uint64_t step_b, float* act_a, float* logp_a, float* obs_out, float* act_b, float* logp_b,
+                          void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------
  * K4  GAE reverse scan. Replaces the block at ppo_continuous.py:198-210.

@@ -20,13 +20,32 @@ namespace {
 using namespace mlp;
 using Smem = mlp::ActorSmem;
 
-template <bool CRITIC>
+// one network's side of a launch: grid.y selects the job, so the pursuer's and the evader's actor (same observations,
+// different weights and Philox step) run as ONE launch - at config-5 shard sizes (8192 envs = 128 CTAs per network) that
+// puts both networks on the GPU at the same time instead of one half-empty launch after the other
+struct ActorJob {
+    const float* packed; const float* eps_in;
+    float *act, *logp, *mean_out, *eps_out, *obs_out, *v_out;
+    uint64_t step;
+    float max_action; int use_tanh;
+};
+struct ActorJobs { ActorJob j[2]; };
+
+template <bool CRITIC, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 2)
-actor_kernel(const float* __restrict__ packed, int use_tanh, float max_action,
-             const float* __restrict__ obs_f32, const SatEnvState st, const double* __restrict__ obs_stats,
-             int64_t n, int64_t row_offset, uint64_t seed, uint64_t step, const float* __restrict__ eps_in,
-             float* __restrict__ act, float* __restrict__ logp, float* __restrict__ mean_out,
-             float* __restrict__ eps_out, float* __restrict__ obs_out, float* __restrict__ v_out) {
+actor_kernel(const __grid_constant__ ActorJobs jobs, const float* __restrict__ obs_f32, const SatEnvState st,
+             const double* __restrict__ obs_stats, int64_t n, int64_t row_offset, uint64_t seed) {
+    // field-by-field select (constant-bank reads): indexing the parameter array with blockIdx.y would copy it to local memory
+    const bool second = PAIR && blockIdx.y != 0;
+#define SAT_JOB(f) (PAIR ? (second ? jobs.j[1].f : jobs.j[0].f) : jobs.j[0].f)
+    const float* __restrict__ packed = SAT_JOB(packed);
+    const int use_tanh = SAT_JOB(use_tanh);
+    const float max_action = SAT_JOB(max_action);
+    const uint64_t step = SAT_JOB(step);
+    const float* __restrict__ eps_in = SAT_JOB(eps_in);
+    float* __restrict__ act = SAT_JOB(act); float* __restrict__ logp = SAT_JOB(logp); float* __restrict__ mean_out = SAT_JOB(mean_out);
+    float* __restrict__ eps_out = SAT_JOB(eps_out); float* __restrict__ obs_out = SAT_JOB(obs_out); float* __restrict__ v_out = SAT_JOB(v_out);
+#undef SAT_JOB
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
@@ -222,11 +241,11 @@ inline int launch_status() {
     return e == cudaSuccess ? SAT_OK : (int)e;
 }
 
-template <bool CRITIC>
+template <bool CRITIC, bool PAIR = false>
 int configure() {
     static int done = 0;     // benign race: idempotent attribute set
     if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(actor_kernel<CRITIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        cudaError_t e = cudaFuncSetAttribute(actor_kernel<CRITIC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return (int)e;
         done = 1;
     }
@@ -259,9 +278,9 @@ int sat_actor_sample(const SatActorWeights* w, const float* obs_f32, const SatEn
     SatEnvState s0 = {};
     if (!obs_f32) s0 = *st;
     const unsigned blocks = (unsigned)((n + M - 1) / M);
-    actor_kernel<false><<<blocks, THREADS, sizeof(Smem), (cudaStream_t)stream>>>(
-        w->packed, w->use_tanh, w->max_action, obs_f32, s0, obs_stats, n, row_offset, seed, step, eps_in,
-        act, logp, mean_out, eps_out, obs_out, nullptr);
+    ActorJobs jobs = {};
+    jobs.j[0] = ActorJob{w->packed, eps_in, act, logp, mean_out, eps_out, obs_out, nullptr, step, w->max_action, w->use_tanh};
+    actor_kernel<false, false><<<dim3(blocks, 1), THREADS, sizeof(Smem), (cudaStream_t)stream>>>(jobs, obs_f32, s0, obs_stats, n, row_offset, seed);
     return launch_status();
 }
 
@@ -273,9 +292,31 @@ int sat_critic_forward(const SatActorWeights* w, const float* obs_f32, int64_t n
     if (rc) return rc;
     SatEnvState s0 = {};
     const unsigned blocks = (unsigned)((n + M - 1) / M);
-    actor_kernel<true><<<blocks, THREADS, sizeof(Smem), (cudaStream_t)stream>>>(
-        w->packed, w->use_tanh, 0.0f, obs_f32, s0, nullptr, n, 0, 0, 0, nullptr,
-        nullptr, nullptr, nullptr, nullptr, nullptr, v);
+    ActorJobs jobs = {};
+    jobs.j[0] = ActorJob{w->packed, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v, 0, 0.0f, w->use_tanh};
+    actor_kernel<true, false><<<dim3(blocks, 1), THREADS, sizeof(Smem), (cudaStream_t)stream>>>(jobs, obs_f32, s0, nullptr, n, 0, 0);
+    return launch_status();
+}
+
+int sat_actor_sample_pair(const SatActorWeights* wa, const SatActorWeights* wb, const float* obs_f32, const SatEnvState* st,
+                          const double* obs_stats, int64_t n, int64_t row_offset, uint64_t seed, uint64_t step_a,
+                          uint64_t step_b, float* act_a, float* logp_a, float* obs_out, float* act_b, float* logp_b,
+                          void* stream) {
+    if (!wa || !wb || !wa->packed || !wb->packed || !act_a || !logp_a || !act_b || !logp_b) return SAT_ERR_NULL;
+    if (!obs_f32 && !(st && st->state)) return SAT_ERR_NULL;
+    if (wa->in_dim != IN || wa->hidden != HID || wa->act_dim != 3 || wb->in_dim != IN || wb->hidden != HID || wb->act_dim != 3)
+        return SAT_ERR_SIZE;
+    if (n <= 0 || (((uintptr_t)wa->packed | (uintptr_t)wb->packed) & 15)) return SAT_ERR_SIZE;
+    if (!obs_f32 && (st->n < n || st->ld < st->n)) return SAT_ERR_SIZE;
+    int rc = configure<false, true>();
+    if (rc) return rc;
+    SatEnvState s0 = {};
+    if (!obs_f32) s0 = *st;
+    const unsigned blocks = (unsigned)((n + M - 1) / M);
+    ActorJobs jobs = {};
+    jobs.j[0] = ActorJob{wa->packed, nullptr, act_a, logp_a, nullptr, nullptr, obs_out, nullptr, step_a, wa->max_action, wa->use_tanh};
+    jobs.j[1] = ActorJob{wb->packed, nullptr, act_b, logp_b, nullptr, nullptr, nullptr, nullptr, step_b, wb->max_action, wb->use_tanh};
+    actor_kernel<false, true><<<dim3(blocks, 2), THREADS, sizeof(Smem), (cudaStream_t)stream>>>(jobs, obs_f32, s0, obs_stats, n, row_offset, seed);
     return launch_status();
 }
 

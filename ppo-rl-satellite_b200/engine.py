@@ -442,6 +442,39 @@ class GaussianActorKernel:
                                           L.ptr(obs_out), L.stream_ptr()), "sat_actor_sample")
         return act, logp
 
+    def sample_pair(self, other, obs=None, env: EnvBatch | None = None, obs_stats: RunningStats | None = None,
+                    seed: int = 0, step: int = 0, other_step: int = 1, row_offset: int = 0, act=None, logp=None,
+                    obs_out=None, other_act=None, other_logp=None):
+        """this actor and `other` on the same observations: exactly self.sample(step=step) and
+        other.sample(step=other_step) -> (act, logp, other_act, other_logp). Up to 32 768 rows both networks go into ONE
+        launch (sat_actor_sample_pair) so that they share the GPU - measured one-launch / two-launch times: 4096 rows 44 / 75
+        us, 8192: 66 / 76, 32 768: 201 / 222; at 65 536 rows each network fills the GPU by itself (388 / 374) and two
+        launches are issued."""
+        torch = self.torch
+        L.guard_device(self.device)
+        if self.w is None or other.w is None:
+            raise L.SatError("weights not loaded")
+        n = obs.shape[0] if obs is not None else env.n
+        if n > 32768:
+            act, logp = self.sample(obs=obs, env=env, obs_stats=obs_stats, seed=seed, step=step, row_offset=row_offset,
+                                    act=act, logp=logp, obs_out=obs_out)
+            other_act, other_logp = other.sample(obs=obs, env=env, obs_stats=obs_stats, seed=seed, step=other_step,
+                                                 row_offset=row_offset, act=other_act, logp=other_logp)
+            return act, logp, other_act, other_logp
+        new = lambda: torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device)
+        act = new() if act is None else act
+        logp = new() if logp is None else logp
+        other_act = new() if other_act is None else other_act
+        other_logp = new() if other_logp is None else other_logp
+        m64 = 2 ** 64 - 1
+        L.check(self.lib.sat_actor_sample_pair(C.byref(self.w), C.byref(other.w), L.ptr(obs),
+                                               C.byref(env.st) if env is not None else None,
+                                               L.ptr(obs_stats.buf) if obs_stats is not None else None, n, int(row_offset),
+                                               int(seed) & m64, int(step) & m64, int(other_step) & m64, L.ptr(act), L.ptr(logp),
+                                               L.ptr(obs_out), L.ptr(other_act), L.ptr(other_logp), L.stream_ptr()),
+                "sat_actor_sample_pair")
+        return act, logp, other_act, other_logp
+
     def value(self, obs, out=None):
         torch = self.torch
         if not self.critic:

@@ -58,10 +58,11 @@ class VectorTrainer:
             self.opponent.sync_kernels()
         for t in range(self.T):
             g = self.t_global
-            self.agent.actor_kernel.sample(env=env, obs_stats=self.obs_stats, seed=self.seed, step=2 * g,
-                                           row_offset=self.row_offset, act=buf.act[t], logp=buf.logp[t], obs_out=buf.obs[t])
-            self.opponent.actor_kernel.sample(env=env, obs_stats=self.obs_stats, seed=self.seed, step=2 * g + 1,
-                                              row_offset=self.row_offset, act=buf.opp_act[t], logp=buf.opp_logp[t])
+            # learner and opponent act on the same observation (CPPO_main.py:122-123): one launch for both networks
+            self.agent.actor_kernel.sample_pair(self.opponent.actor_kernel, env=env, obs_stats=self.obs_stats, seed=self.seed,
+                                                step=2 * g, other_step=2 * g + 1, row_offset=self.row_offset, act=buf.act[t],
+                                                logp=buf.logp[t], obs_out=buf.obs[t], other_act=buf.opp_act[t],
+                                                other_logp=buf.opp_logp[t])
             pa, ea = (buf.act[t], buf.opp_act[t]) if self.learner_is_pursuer else (buf.opp_act[t], buf.act[t])
             env.step(pa, ea, reward=buf.rew64[t], done=buf.done[t], obs_stats=self.obs_stats, ret_stats=self.ret_stats,
                      ret_std_out=buf.ret_std[t:t + 1] if self.ret_stats is not None else None)

@@ -674,3 +674,26 @@ def test_step_timed_is_the_same_step(eng):
         assert len(ms) == 3 and ms[0] > 0 and ms[1] > 0
         assert torch.equal(ra, b.reward) and torch.equal(da, b.done)
     assert torch.equal(a.state, b.state) and torch.equal(a.istate, b.istate)
+
+
+def test_actor_sample_pair_equals_two_calls(golden, eng):
+    """sat_actor_sample_pair: both networks in one launch, bit-identical to two sat_actor_sample calls"""
+    g = golden("ppo_golden.npz")
+    W = _weights(g, "actor.")
+    a = eng.GaussianActorKernel().load_state_dict(W)
+    W2 = {k: (v * 0.9 + 0.01) for k, v in W.items()}
+    b = eng.GaussianActorKernel().load_state_dict(W2)
+    for n in (1, 63, 1000):
+        env = eng.EnvBatch(n, mode="cw")
+        rng = np.random.default_rng(n)
+        env.set_state(np.array([2e5, 0, 0]) + rng.normal(0, 3e4, (n, 3)), rng.normal(0, 3, (n, 3)),
+                      np.array([1.8e4, 0, 0]) + rng.normal(0, 3e4, (n, 3)), rng.normal(0, 3, (n, 3)))
+        stats = eng.RunningStats(18)
+        stats.update_normalize(env.observe())
+        obs1 = torch.empty((n, 18), dtype=torch.float32, device="cuda"); obs2 = torch.empty_like(obs1)
+        a1, l1 = a.sample(env=env, obs_stats=stats, seed=3, step=10, row_offset=7, obs_out=obs1)
+        b1, m1 = b.sample(env=env, obs_stats=stats, seed=3, step=11, row_offset=7)
+        a2, l2, b2, m2 = a.sample_pair(b, env=env, obs_stats=stats, seed=3, step=10, other_step=11, row_offset=7, obs_out=obs2)
+        for x, y in ((a1, a2), (l1, l2), (b1, b2), (m1, m2), (obs1, obs2)):
+            assert torch.equal(x, y)
+        assert not torch.equal(a1, b1)
