@@ -205,11 +205,20 @@ env_front_rk4_kernel(const SatEnvState st, const ActT* __restrict__ pa, const Ac
 struct SolveQueue {
     double A[2 * kBlock], sth[2 * kBlock], dvm[2 * kBlock], alpha[2 * kBlock];
     int guess[2 * kBlock];
+    double trig[2][4];      // per guess: sin, cos at x0 and at x0 + sqrt(eps)|x0| (Hybrd1::init_warm)
     int count, next;
 };
 
 SAT_DEV void queue_init(SolveQueue& q) {
     if (threadIdx.x == 0) { q.count = 0; q.next = 0; }
+    if (threadIdx.x < 4) {
+        const int j = threadIdx.x >> 1, k = threadIdx.x & 1;
+        const double x0 = dz_guess(j);
+        const double h = 1.4901161193847656e-08 * fabs(x0);           // Hybrd1::start_outer
+        double sv, cv;
+        sincos(k ? x0 + h : x0, &sv, &cv);
+        q.trig[j][2 * k] = sv; q.trig[j][2 * k + 1] = cv;
+    }
     __syncthreads();
 }
 
@@ -247,7 +256,7 @@ SAT_DEV void queue_run(SolveQueue& q) {
             if (t < total) {
                 task = t;
                 PFai f; f.A = q.A[t]; f.sth = q.sth[t]; f.dvm = q.dvm[t];
-                hs.init(f, dz_guess(q.guess[t]));
+                hs.init_warm(f, dz_guess(q.guess[t]), q.trig[q.guess[t]]);
             } else task = total;                     // queue drained for this lane
         }
         const bool active = task < total;

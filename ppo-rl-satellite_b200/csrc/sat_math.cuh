@@ -179,10 +179,11 @@ SAT_DEV bool orbital_elements(double miu, const double R0[3], const double V0[3]
 // ------------------------------------------------------------------------------------------
 struct PFai {
     double A, sth, dvm;
+    SAT_DEV double at(double s, double c) const { return A * (dvm * c) + sth * (-dvm * s); }   // given sin, cos of alpha
     SAT_DEV double operator()(double alpha) const {
         double s, c;
         sincos(alpha, &s, &c);
-        return A * (dvm * c) + sth * (-dvm * s);
+        return at(s, c);
     }
 };
 
@@ -239,13 +240,22 @@ struct Hybrd1 {
         if (iter == 1) delta = fmin(delta, pnorm);
         phase = 2;
     }
-    // one function evaluation + bookkeeping; returns true when finished (root estimate in x).
+    // step(): one function evaluation + bookkeeping; returns true when finished (root estimate in x).
     // Single evaluation site and single dogleg site: lanes in different phases share both.
-    SAT_DEV bool step() {
+    SAT_DEV double next_x() const { return (phase == 0) ? x : ((phase == 1) ? x + h : xt); }
+    SAT_DEV bool step() { return consume(f(next_x())); }
+    // Warm start for a known initial guess: the first two evaluation points of hybrd (x0, then x0 + sqrt(eps)|x0| for the
+    // forward-difference Jacobian) depend on the guess only, so the caller supplies sin/cos at those two points (computed
+    // once per CTA with the same sincos) and the two trips through the shared evaluation site are saved. Same arithmetic.
+    SAT_DEV void init_warm(const F& fn, double x0, const double sc[4]) {
+        init(fn, x0);
+        consume(f.at(sc[0], sc[1]));          // phase 0: f(x0)
+        consume(f.at(sc[2], sc[3]));          // phase 1: f(x0 + h); never finishes, leaves the first trial point in xt
+    }
+    // bookkeeping for the value fe of f at next_x(); returns true when finished (root estimate in x)
+    SAT_DEV bool consume(const double fe) {
         const double epsmch = 2.220446049250313e-16, xtol = 1.49012e-08, factor = 100.0;
         const int maxfev = 400;
-        const double xe = (phase == 0) ? x : ((phase == 1) ? x + h : xt);
-        const double fe = f(xe);
         ++nfev;
         bool need_dogleg = false, finished = false;
         if (phase == 0) { fv = fe; fnorm = fabs(fv); start_outer(); }
