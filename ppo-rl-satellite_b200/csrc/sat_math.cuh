@@ -282,7 +282,8 @@ struct Hybrd1 {
             const double pred = qtf + r * p;
             const double qp = zdiv(fabs(pred), fnorm);
             const double prered = (fabs(pred) < fnorm) ? 1.0 - qp * qp : 0.0;
-            const double ratio = (prered > 0.0) ? actred / prered : 0.0;
+            // prered == 1 exactly whenever the predicted residual is 0 (the usual full Newton step): x / 1 == x
+            const double ratio = (prered > 0.0) ? ((prered == 1.0) ? actred : actred / prered) : 0.0;
             if (ratio < 0.1) { ncsuc = 0; ++ncfail; delta = 0.5 * delta; }
             else {
                 ncfail = 0; ++ncsuc;
@@ -299,7 +300,11 @@ struct Hybrd1 {
             else if (nslow2 == 5 || nslow1 == 10) finished = true;                          // info 4 / 5
             else if (ncfail == 2) start_outer();                                            // re-evaluate the Jacobian
             else {
-                const double s = q * ft, v = (s - pred) / pnorm, uu = d * ((d * p) / pnorm);   // Broyden rank-1 update
+                // Broyden rank-1 update. pnorm is |d p| from the dogleg step with these same d and p, so (d p) / pnorm is
+                // exactly +-1 for every finite non-zero d p: one IEEE division less per trial step, same bits
+                const double dp = d * p;
+                const double sgn = (dp != 0.0 && fabs(dp) <= 1.7976931348623157e308) ? copysign(1.0, dp) : dp / pnorm;
+                const double s = q * ft, v = (s - pred) / pnorm, uu = d * sgn;
                 if (ratio >= 1e-4) qtf = s;
                 r = r + uu * v; jeval = false;
                 need_dogleg = true;
