@@ -134,6 +134,24 @@ int sat_env_step_timed(const SatEnvState* st, const void* pa, const void* ea, co
 int sat_danger_zone_count(const double* rv, const double* dv, int64_t n, double u_grav, int32_t* count_out,
                           double* debug_out, void* stream);
 
+/* batched Numerical_iteration_method(u, Delta_Vm, theta, v_1x, v_1y, h, alpha_guess) (satellite_function.py:558-565):
+ * one scipy.optimize.fsolve (MINPACK hybrd, n = 1) root of P_fai_equation per element, returned un-polished like the
+ * reference's result[0]. All arrays [n] fp64 on the device; nfev_out (nullable) [n] int32 = function evaluations. */
+int sat_fsolve_pfai(const double* dvm, const double* theta, const double* v1x, const double* v1y, const double* h,
+                    const double* guess, int64_t n, double u_grav, double* root_out, int32_t* nfev_out, void* stream);
+
+/* elementwise evaluation of the device libm the danger-zone path uses (csrc/glibm.cuh), so tests can compare it bit for
+ * bit with the host libm the reference calls: fn = SAT_LIBM_SIN / COS / ACOS / ATAN / POW2 (numpy scalar sin, cos,
+ * arccos, arctan and python `x ** 2`), SINCOS_S / SINCOS_C = the fused form's two outputs. x, y [n] fp64 on the device. */
+#define SAT_LIBM_SIN 0
+#define SAT_LIBM_COS 1
+#define SAT_LIBM_ACOS 2
+#define SAT_LIBM_ATAN 3
+#define SAT_LIBM_POW2 4
+#define SAT_LIBM_SINCOS_S 5
+#define SAT_LIBM_SINCOS_C 6
+int sat_libm_eval(int fn, const double* x, double* y, int64_t n, void* stream);
+
 /* host-buffer form of step(): actions from (pinned) host memory, obs_f32/reward/done to host memory, synchronised
  * before returning. d_io is a caller-provided device staging buffer of sat_env_step_host_bytes(n) bytes.
  * With aux_stream != NULL and chunks > 1 (<= 16) the batch is cut into env ranges that alternate between `stream` and

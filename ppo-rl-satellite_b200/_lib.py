@@ -85,6 +85,8 @@ SIGNATURES = {
     "sat_env_step_timed": (C.c_int, [C.POINTER(SatEnvState), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                      C.POINTER(SatEnvParams), _P, _P]),
     "sat_danger_zone_count": (C.c_int, [_P, _P, _I64, _D, _P, _P, _P]),
+    "sat_fsolve_pfai": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _D, _P, _P, _P]),
+    "sat_libm_eval": (C.c_int, [_I32, _P, _P, _I64, _P]),
     "sat_env_step_host_bytes": (_I64, [_I64]),
     "sat_env_step_host": (C.c_int, [C.POINTER(SatEnvState), _P, _P, _P, _P, _P, _P, C.POINTER(SatEnvParams), _P, _P, _I32]),
     "sat_norm_update": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P]),

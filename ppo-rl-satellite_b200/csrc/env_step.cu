@@ -216,7 +216,7 @@ SAT_DEV void queue_init(SolveQueue& q) {
         const double x0 = dz_guess(j);
         const double h = 1.4901161193847656e-08 * fabs(x0);           // Hybrd1::start_outer
         double sv, cv;
-        sincos(k ? x0 + h : x0, &sv, &cv);
+        glibm::sincos(k ? x0 + h : x0, &sv, &cv);
         q.trig[j][2 * k] = sv; q.trig[j][2 * k + 1] = cv;
     }
     __syncthreads();
@@ -521,6 +521,44 @@ danger_zone_kernel(const double* __restrict__ rv, const double* __restrict__ dv,
             o[5] = dbg.theta; o[6] = dbg.dvm; o[7] = dbg.f_cx;
         }
     }
+}
+
+// one fsolve per thread, straight-line form of the same Hybrd1<PFai> the env step runs (satellite_function.py:558-565)
+__global__ void __launch_bounds__(kBlock)
+fsolve_pfai_kernel(const double* __restrict__ dvm, const double* __restrict__ theta, const double* __restrict__ v1x,
+                   const double* __restrict__ v1y, const double* __restrict__ h, const double* __restrict__ guess,
+                   int64_t n, double u_grav, double* __restrict__ root_out, int32_t* __restrict__ nfev_out) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    double sth, cth;
+    glibm::sincos(theta[i], &sth, &cth);
+    PFai f;
+    f.A = (2.0 * u_grav * (1.0 - cth)) / (h[i] * v1y[i]) - v1x[i] * sth / v1y[i];      // :560
+    f.sth = sth;
+    f.dvm = dvm[i];
+    Hybrd1<PFai> hs;
+    hs.init(f, guess[i]);
+    while (!hs.step()) {}
+    root_out[i] = hs.x;
+    if (nfev_out) nfev_out[i] = hs.nfev;
+}
+
+__global__ void __launch_bounds__(256)
+libm_eval_kernel(int fn, const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r = 0.0, s, c;
+    switch (fn) {
+        case SAT_LIBM_SIN: r = glibm::sin(v); break;
+        case SAT_LIBM_COS: r = glibm::cos(v); break;
+        case SAT_LIBM_ACOS: r = glibm::acos(v); break;
+        case SAT_LIBM_ATAN: r = glibm::atan(v); break;
+        case SAT_LIBM_POW2: r = glibm::pow2(v); break;
+        case SAT_LIBM_SINCOS_S: glibm::sincos(v, &s, &c); r = s; break;
+        default: glibm::sincos(v, &s, &c); r = c; break;
+    }
+    y[i] = r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -879,6 +917,23 @@ int sat_danger_zone_count(const double* rv, const double* dv, int64_t n, double 
     if (n <= 0) return SAT_ERR_SIZE;
     const int64_t nblocks = (n + kEnvsPerBlock - 1) / kEnvsPerBlock;
     danger_zone_kernel<<<(unsigned)nblocks, kBlock, 0, (cudaStream_t)stream>>>(rv, dv, n, u_grav, count_out, debug_out);
+    return launch_status();
+}
+
+int sat_fsolve_pfai(const double* dvm, const double* theta, const double* v1x, const double* v1y, const double* h,
+                    const double* guess, int64_t n, double u_grav, double* root_out, int32_t* nfev_out, void* stream) {
+    if (!dvm || !theta || !v1x || !v1y || !h || !guess || !root_out) return SAT_ERR_NULL;
+    if (n <= 0) return SAT_ERR_SIZE;
+    fsolve_pfai_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        dvm, theta, v1x, v1y, h, guess, n, u_grav, root_out, nfev_out);
+    return launch_status();
+}
+
+int sat_libm_eval(int fn, const double* x, double* y, int64_t n, void* stream) {
+    if (!x || !y) return SAT_ERR_NULL;
+    if (n <= 0) return SAT_ERR_SIZE;
+    if (fn < SAT_LIBM_SIN || fn > SAT_LIBM_SINCOS_C) return SAT_ERR_MODE;
+    libm_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fn, x, y, n);
     return launch_status();
 }
 

@@ -8,9 +8,13 @@
 //       count (106 per RK4+J2 step), whose parity bar is 1e-9 relative, not bit identity.
 // Translation units that include this file are compiled with -fmad=false, so every fused
 // operation in the binary is one that is spelled fma() here.
+//   (3) the transcendental calls of the danger-zone path (sin, cos, acos, atan, and python's `x ** 2` = pow(x, 2.0))
+//       go through glibm.cuh, a restatement of the host libm the reference runs on, because the integer danger-zone
+//       count depends on their last bit.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "glibm.cuh"
 
 #define SAT_DEV __device__ __forceinline__
 
@@ -145,7 +149,7 @@ struct Elements { double a, e, i, omega, Omega, f; };
 SAT_DEV bool orbital_elements(double miu, const double R0[3], const double V0[3], Elements& el) {
     double r_norm = norm3(R0), v_norm = norm3(V0);                       // :183-184
     double r_dot_v = dot3(R0, V0);                                       // :185
-    double v2 = v_norm * v_norm;
+    double v2 = glibm::pow2(v_norm);                                     // v_norm ** 2 (:186, :193)
     double energy = 2.0 / r_norm - v2 / miu;                             // :186
     double c1 = v2 / miu - 1.0 / r_norm, c2 = r_dot_v / miu;             // :193
     double E[3], H[3], N[3];
@@ -159,14 +163,14 @@ SAT_DEV bool orbital_elements(double miu, const double R0[3], const double V0[3]
     if (energy == 0.0 || e == 0.0) return false;
     el.a = 1.0 / fabs(energy);                                           // :188
     el.e = e;
-    el.i = acos(H[2] / h);                                               // :210
-    double omega = (n != 0.0) ? acos(dot3(N, E) / n / e) : 0.0;          // :214-217
+    el.i = glibm::acos(H[2] / h);                                               // :210
+    double omega = (n != 0.0) ? glibm::acos(dot3(N, E) / n / e) : 0.0;          // :214-217
     if (E[2] < 0.0) omega = kTwoPi - omega;                              // :221
     el.omega = omega;
-    double Omega = (n != 0.0) ? acos(N[0] / n) : 0.0;                    // :230-233
+    double Omega = (n != 0.0) ? glibm::acos(N[0] / n) : 0.0;                    // :230-233
     if (N[1] < 0.0) Omega = kTwoPi - Omega;                              // :237
     el.Omega = Omega;
-    double f = acos(dot3(E, R0) / e / r_norm);                           // :242
+    double f = glibm::acos(dot3(E, R0) / e / r_norm);                           // :242
     if (r_dot_v < 0.0) f = kTwoPi - f;
     el.f = f;
     return true;
@@ -182,7 +186,7 @@ struct PFai {
     SAT_DEV double at(double s, double c) const { return A * (dvm * c) + sth * (-dvm * s); }   // given sin, cos of alpha
     SAT_DEV double operator()(double alpha) const {
         double s, c;
-        sincos(alpha, &s, &c);
+        glibm::sincos(alpha, &s, &c);
         return at(s, c);
     }
 };
@@ -363,21 +367,21 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     const Elements& t = craft == 0 ? el_oth : el_own;     // target
     // calculate_latitudinal_angle, satellite_function.py:326-337
     double si_t, ci_t, si_c, ci_c, sdo, cdo, sdo2, cdo2;
-    sincos(t.i, &si_t, &ci_t); sincos(c.i, &si_c, &ci_c);
-    sincos(c.Omega - t.Omega, &sdo, &cdo);
+    glibm::sincos(t.i, &si_t, &ci_t); glibm::sincos(c.i, &si_c, &ci_c);
+    glibm::sincos(c.Omega - t.Omega, &sdo, &cdo);
     sdo2 = -sdo; cdo2 = cdo;          // sin/cos of (Omega_t - Omega_c) = -(Omega_c - Omega_t): exact odd/even symmetry
     double temp1 = (si_t * sdo) / (ci_t * si_c - si_t * ci_c * cdo);
     double temp2 = (si_c * sdo2) / (ci_c * si_t - si_c * ci_t * cdo2);
     if (isnan(temp1) || isnan(temp2)) { temp1 = 1.0; temp2 = 1.0; }      // :331-332
-    const double u_c1 = atan(temp1), u_t1 = atan(temp2);
+    const double u_c1 = glibm::atan(temp1), u_t1 = glibm::atan(temp2);
     // :352-355; lane 0 -> node 1 (f_c1, r_ft1 uses f_t2), lane 1 -> node 2 (f_c2, r_ft2 uses f_t1) (Q5)
     const double f_cx = (craft == 0 ? u_c1 : kPi + u_c1) - c.omega;
     const double f_tx = (craft == 0 ? u_t1 + kPi : u_t1) - t.omega;
     nd.f_cx = f_cx;
-    nd.r_ft = (t.a * (1.0 - t.e * t.e)) / (1.0 + t.e * cos(f_tx));       // :363 / :365
-    const double one_m_e2 = 1.0 - c.e * c.e;
+    nd.r_ft = (t.a * (1.0 - glibm::pow2(t.e))) / (1.0 + t.e * glibm::cos(f_tx));       // :363 / :365
+    const double one_m_e2 = 1.0 - glibm::pow2(c.e);
     double sf0, cf0;
-    sincos(c.f, &sf0, &cf0);
+    glibm::sincos(c.f, &sf0, &cf0);
     const double k = 1.0 + c.e * cf0;
     const double r_c = c.a * one_m_e2 / k;                                // :57
     const double p_c = c.a * one_m_e2;                                    // :58
@@ -385,31 +389,32 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     // rf_extreme_point, satellite_function.py:462-494 with fai = 0
     const double df = f_cx - c.f;
     double sdf, cdf;
-    sincos(df, &sdf, &cdf);
-    const double tmp1 = (sdf * sdf) / (u_grav * (k * k) / (p_c * (dv * dv)) - 1.0);   // :466 / :481
+    glibm::sincos(df, &sdf, &cdf);
+    const double k2 = glibm::pow2(k), dv2 = glibm::pow2(dv);
+    const double tmp1 = glibm::pow2(sdf) / (u_grav * k2 / (p_c * dv2) - 1.0);   // :466 / :481
     if (!(0.0 <= tmp1)) { nd.status = 1; return; }                                    // :478 -> (0, 0)
     // :469-470 with tan(fai) = 0: beta = atan(+-0 / sdf) = +-0 for every finite non-zero sdf, so cos(beta) = 1 and the
     // subtracted term u k^2 sin(beta)^2 / p_c is +-0 (u k^2 finite, p_c non-zero): dvm = sqrt(dv^2) bit for bit. The general
     // form stays for the other inputs; the shortcut keeps a zero-numerator division (warp-wide slow path), an atan and a
     // sincos off the common path.
     double cb, dvm;
-    if (sdf != 0.0 && fabs(sdf) <= 1.0 && fabs(u_grav * (k * k)) <= 1.7976931348623157e308 && p_c != 0.0 && p_c == p_c) {
+    if (sdf != 0.0 && fabs(sdf) <= 1.0 && fabs(u_grav * k2) <= 1.7976931348623157e308 && p_c != 0.0 && p_c == p_c) {
         cb = 1.0;
-        dvm = sqrt(dv * dv);
+        dvm = sqrt(dv2);
     } else {
-        const double beta = atan(0.0 / sdf);                                          // :469
+        const double beta = glibm::atan(0.0 / sdf);                                          // :469
         double sb;
-        sincos(beta, &sb, &cb);
-        dvm = sqrt(dv * dv - u_grav * (k * k) * (sb * sb) / p_c);                     // :470
+        glibm::sincos(beta, &sb, &cb);
+        dvm = sqrt(dv2 - u_grav * k2 * glibm::pow2(sb) / p_c);                     // :470
     }
     // :464, :473-476 (theta stays 0 outside both ranges, Q5). One acos for the warp, the range decides how it is used:
     // an if / else-if around two acos calls made every warp run the routine twice with part of its lanes.
-    const double ac = acos(cdf * 1.0);
+    const double ac = glibm::acos(cdf * 1.0);
     const bool in_a = (-kTwoPi <= df && df < -kPi) || (0.0 <= df && df < kPi);
     const bool in_b = (-kPi <= df && df < 0.0) || (kPi <= df && df < kTwoPi);
     const double theta = in_a ? ac : (in_b ? kTwoPi - ac : 0.0);
     double sth, cth;
-    sincos(theta, &sth, &cth);
+    glibm::sincos(theta, &sth, &cth);
     const double sq = sqrt(u_grav / p_c);
     const double sq_e_sin = sq * c.e * sf0;                                           // :518 first term
     const double sq_k = sq * k * cb;                                                  // :519 first term
@@ -418,7 +423,7 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     for (int j = 0; j < 2; ++j) {
         const double ag = (j == 0) ? kPi / 2 : -kPi / 2;                              // :516 / :534
         double sg, cg;
-        sincos(ag, &sg, &cg);
+        glibm::sincos(ag, &sg, &cg);
         const double v1x = sq_e_sin + dvm * cg;
         const double v1y = sq_k + dvm * sg;
         const double h = r_c * v1y;                                                   // :521
@@ -442,11 +447,11 @@ SAT_DEV bool dz_degenerate(double A, double sth, double dvm) { return A == 0.0 &
 
 SAT_DEV double dz_rf(const DzNode& nd, double alpha) {
     double s, c;
-    sincos(alpha, &s, &c);
+    glibm::sincos(alpha, &s, &c);
     const double v1x = nd.sq_e_sin + nd.dvm * c;                                      // :525 / :541
     const double v1y = nd.sq_k + nd.dvm * s;                                          // :526 / :542
     const double hm = nd.r_c * v1y;
-    return fabs((hm * hm) / (nd.u * (1.0 - nd.cth) + hm * v1y * nd.cth - hm * v1x * nd.sth));   // :530 / :545, :549-550
+    return fabs(glibm::pow2(hm) / (nd.u * (1.0 - nd.cth) + hm * v1y * nd.cth - hm * v1x * nd.sth));   // :530 / :545, :549-550
 }
 
 // returns 0/1/2, or -1 when the reference would raise; alpha0/alpha1 are ignored unless nd.status == 2

@@ -368,6 +368,32 @@ def danger_zone_count(rv, dv, u=MU_M, debug=False):
     return (out, dbg) if debug else out
 
 
+def numerical_iteration(dvm, theta, v1x, v1y, h, guess, u=MU_M, return_nfev=False):
+    """Batched Time_window_of_danger_zone.Numerical_iteration_method (satellite_function.py:558-565): one
+    scipy.optimize.fsolve root of P_fai_equation per element. CUDA fp64 [n] arrays -> roots [n] (un-polished result[0])."""
+    torch = L.require_cuda()
+    args = [a.contiguous() for a in (dvm, theta, v1x, v1y, h, guess)]
+    n = args[0].shape[0]
+    root = torch.empty(n, dtype=torch.float64, device=args[0].device)
+    nfev = torch.empty(n, dtype=torch.int32, device=args[0].device) if return_nfev else None
+    L.check(L.load().sat_fsolve_pfai(*[L.ptr(a) for a in args], n, float(u), L.ptr(root), L.ptr(nfev), L.stream_ptr()),
+            "sat_fsolve_pfai")
+    return (root, nfev) if return_nfev else root
+
+
+LIBM_FN = {"sin": 0, "cos": 1, "acos": 2, "atan": 3, "pow2": 4, "sincos_s": 5, "sincos_c": 6}
+
+
+def libm_eval(fn: str, x):
+    """The device libm of the danger-zone path (csrc/glibm.cuh: numpy scalar sin / cos / arccos / arctan, python x ** 2)
+    evaluated elementwise on a CUDA fp64 tensor; exists so tests can compare it bit for bit with the host libm."""
+    torch = L.require_cuda()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    L.check(L.load().sat_libm_eval(LIBM_FN[fn], L.ptr(x), L.ptr(y), x.numel(), L.stream_ptr()), "sat_libm_eval")
+    return y
+
+
 def reachable_domain(elements, delta_max, N2=200, N3=200, u=MU_M):
     """Batched RD_single_pulse.Reachable_Domain sweep. elements: CUDA fp64 [n,6] (a,e,i,omega,Omega,f); delta_max [n].
     -> rf_max [n,D,3], rf_min [n,D,3], valid [n,D] (uint8), D = (N2+1)*(N3+1) directions in the reference's loop order."""
