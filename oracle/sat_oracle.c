@@ -18,7 +18,8 @@
 
 #define ORC_PI 3.141592653589793
 /* python/numpy scalar `x ** 2` is libm pow(x, 2.0), which is NOT always equal to x*x (glibc pow is
- * not correctly rounded: 90 of 1e5 random squares differ by one ulp). Keep the call. */
+ * not correctly rounded: 90 of 1e5 random squares differ by one ulp). Keep the call: the Makefile passes
+ * -fno-builtin-pow so that GCC does not fold it into x*x. */
 #define SQ(x) pow((x), 2.0)
 
 /* ------------------------------------------------------------------------------------------

@@ -194,6 +194,23 @@ def test_danger_zone_counts_vs_reference_golden(golden, eng):
     assert bad == 0, bad
 
 
+def test_orbital_elements_bit_identical_to_oracle(oracle, eng):
+    """calculate_orbital_elements (satellite_function.py:161-255) on 100 000 random near-GEO states: all six elements bit for
+    bit (acos through the device libm, v_norm ** 2 through the device pow; the element a is a 1-ulp detector for the latter)."""
+    from ppo_rl_satellite_b200 import _lib as L
+    rng = np.random.default_rng(0)
+    n = 100000
+    rv = np.concatenate([np.array([27098000.0, 32306000.0, 0.0]) + rng.normal(0, 1e5, (n, 3)),
+                         np.array([-2350.0, 1970.0, 0.0]) + rng.normal(0, 20, (n, 3))], axis=1)
+    d_rv = torch.from_numpy(rv).cuda()
+    out = torch.empty_like(d_rv)
+    kind = torch.empty(n, dtype=torch.int32, device="cuda")
+    L.check(L.load().sat_orbital_elements(d_rv.data_ptr(), n, 3.986e14, out.data_ptr(), kind.data_ptr(), L.stream_ptr()), "elements")
+    want = np.array([oracle.orbital_elements(3.986e14, rv[i, 0:3], rv[i, 3:6])[:6] for i in range(n)])
+    bad = (out.cpu().numpy().view(np.int64) != want.view(np.int64)).sum(axis=0)
+    assert bad.sum() == 0, bad
+
+
 def test_fsolve_roots_bit_identical_to_reference_golden(golden, eng):
     """The 4000 Numerical_iteration_method calls recorded from the reference (scipy.optimize.fsolve roots,
     satellite_function.py:558-565) through the DEVICE hybrd + device libm: every root bit for bit."""

@@ -1,6 +1,7 @@
 """Large-sample parity soak (cw mode, the env as shipped): N envs x T steps on the GPU against the CPU oracle with the same
-random fp32 actions. Reports the danger-zone flip rate (the one documented non-bit-exact place) and checks that every env
-that has not flipped is bit-identical in observation, reward and done. Writes gpurun_out/soak_parity.txt."""
+random fp32 actions. Reports the number of envs whose integer danger-zone count ever differed from the oracle (target 0) and
+checks that every other env is bit-identical in observation, reward and done. Every differing evaluation is re-run through
+sat_danger_zone_count / the oracle's debug entry and dumped. Writes gpurun_out/soak_parity.txt (+ soak_flips.npz)."""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,6 +13,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 g = np.load(os.path.join(ROOT, "tests/golden/env_golden.npz"))
 out = []
+Rcw = np.array([27098000.0, 32306000.0, 0.0]); Vcw = np.array([-2350.0, 1970.0, 0.0])
+flip_states, flip_fuel = [], []
 for flag in (0, 1):
     kw = dict(d_capture=181200.0, max_episode_steps=40, flag=flag)
     env = eng.EnvBatch(n, mode="cw", auto_reset=True, stm=g["stm100_columns"], **kw)
@@ -28,6 +31,11 @@ for flag in (0, 1):
         dz, o_dz = env.dangerous_zone.cpu().numpy(), orc.aux()[3]
         dn = d.cpu().numpy().astype(bool)
         evals += int((~dn).sum()); dones += int(dn.sum())
+        new = (dz != o_dz) & ~flipped & ~dn
+        if new.any():
+            o = o_obs[new]
+            flip_states.append(np.concatenate([Rcw + o[:, 6:9], Vcw + o[:, 9:12], Rcw + o[:, 12:15], Vcw + o[:, 15:18]], axis=1))
+            flip_fuel.append(env.fuel_c.cpu().numpy()[new])
         flipped |= dz != o_dz
         ok = ~flipped
         same = (np.array_equal(dn[ok], o_d[ok].astype(bool)) and np.array_equal(r.cpu().numpy()[ok], o_r[ok])
@@ -38,4 +46,14 @@ for flag in (0, 1):
             f"non-flipped env differed in obs/reward/done: {bad}; {time.time() - t0:.0f} s")
     print(line, flush=True); out.append(line)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+if flip_states:
+    bs, bf = np.concatenate(flip_states), np.concatenate(flip_fuel)
+    cnt, dbg = eng.danger_zone_count(torch.from_numpy(bs).cuda(), torch.from_numpy(bf).cuda(), debug=True)
+    odbg = [O.danger_zone_debug(bs[i, 0:3], bs[i, 3:6], bs[i, 6:9], bs[i, 9:12], bf[i]) for i in range(len(bs))]
+    np.savez(os.path.join(ROOT, "gpurun_out", "soak_flips.npz"), states=bs, fuel=bf, dev_cnt=cnt.cpu().numpy(), dev_dbg=dbg.cpu().numpy(),
+             orc_cnt=np.array([c for c, _ in odbg]), orc_dbg=np.array([d for _, d in odbg]))
+    np.set_printoptions(precision=17, linewidth=220)
+    for i in range(min(8, len(bs))):
+        line = f"flip {i}: standalone device count {int(cnt[i])}, oracle {odbg[i][0]}, fuel {bf[i]!r}\n dev {dbg[i].cpu().numpy()}\n orc {odbg[i][1]}"
+        print(line, flush=True); out.append(line)
 open(os.path.join(ROOT, "gpurun_out", "soak_parity.txt"), "w").write("\n".join(out) + "\n")
