@@ -215,9 +215,8 @@ SAT_DEV void queue_init(SolveQueue& q) {
         const int j = threadIdx.x >> 1, k = threadIdx.x & 1;
         const double x0 = dz_guess(j);
         const double h = 1.4901161193847656e-08 * fabs(x0);           // Hybrd1::start_outer
-        double sv, cv;
-        glibm::sincos(k ? x0 + h : x0, &sv, &cv);
-        q.trig[j][2 * k] = sv; q.trig[j][2 * k + 1] = cv;
+        const double2 sc = glibm::call::sincos(k ? x0 + h : x0);
+        q.trig[j][2 * k] = sc.x; q.trig[j][2 * k + 1] = sc.y;
     }
     __syncthreads();
 }

@@ -391,4 +391,17 @@ GLIBM_FN double pow2(double x) {
     return fma_(tmp2, scale, scale);
 }
 
+#if defined(__CUDACC__)
+// Out-of-line copies for straight-line device code with many call sites (orbital elements, danger-zone set-up): one
+// body per function keeps the kernel inside the instruction cache (inlined everywhere the danger-zone kernel grew to
+// 15 000 SASS instructions and stalled on instruction fetch). Results come back in registers.
+namespace call {
+static __device__ __noinline__ double2 sincos(double x) { double s, c; glibm::sincos(x, &s, &c); return make_double2(s, c); }
+static __device__ __noinline__ double cos(double x) { return glibm::cos(x); }
+static __device__ __noinline__ double acos(double x) { return glibm::acos(x); }
+static __device__ __noinline__ double atan(double x) { return glibm::atan(x); }
+static __device__ __noinline__ double pow2(double x) { return glibm::pow2(x); }
+}  // namespace call
+#endif
+
 }  // namespace glibm

@@ -149,7 +149,7 @@ struct Elements { double a, e, i, omega, Omega, f; };
 SAT_DEV bool orbital_elements(double miu, const double R0[3], const double V0[3], Elements& el) {
     double r_norm = norm3(R0), v_norm = norm3(V0);                       // :183-184
     double r_dot_v = dot3(R0, V0);                                       // :185
-    double v2 = glibm::pow2(v_norm);                                     // v_norm ** 2 (:186, :193)
+    double v2 = glibm::call::pow2(v_norm);                                     // v_norm ** 2 (:186, :193)
     double energy = 2.0 / r_norm - v2 / miu;                             // :186
     double c1 = v2 / miu - 1.0 / r_norm, c2 = r_dot_v / miu;             // :193
     double E[3], H[3], N[3];
@@ -163,14 +163,14 @@ SAT_DEV bool orbital_elements(double miu, const double R0[3], const double V0[3]
     if (energy == 0.0 || e == 0.0) return false;
     el.a = 1.0 / fabs(energy);                                           // :188
     el.e = e;
-    el.i = glibm::acos(H[2] / h);                                               // :210
-    double omega = (n != 0.0) ? glibm::acos(dot3(N, E) / n / e) : 0.0;          // :214-217
+    el.i = glibm::call::acos(H[2] / h);                                               // :210
+    double omega = (n != 0.0) ? glibm::call::acos(dot3(N, E) / n / e) : 0.0;          // :214-217
     if (E[2] < 0.0) omega = kTwoPi - omega;                              // :221
     el.omega = omega;
-    double Omega = (n != 0.0) ? glibm::acos(N[0] / n) : 0.0;                    // :230-233
+    double Omega = (n != 0.0) ? glibm::call::acos(N[0] / n) : 0.0;                    // :230-233
     if (N[1] < 0.0) Omega = kTwoPi - Omega;                              // :237
     el.Omega = Omega;
-    double f = glibm::acos(dot3(E, R0) / e / r_norm);                           // :242
+    double f = glibm::call::acos(dot3(E, R0) / e / r_norm);                           // :242
     if (r_dot_v < 0.0) f = kTwoPi - f;
     el.f = f;
     return true;
@@ -351,6 +351,9 @@ struct DzNode {
 
 SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double Vi[3], double fuel_c,
                         double u_grav, DzNode& nd) {
+    nd.status = 0; nd.dvm = 0.0; nd.theta = 0.0; nd.f_cx = 0.0; nd.r_ft = 0.0;
+    nd.A0 = 0.0; nd.A1 = 0.0; nd.sth = 0.0; nd.cth = 1.0; nd.sq_e_sin = 0.0; nd.sq_k = 0.0; nd.r_c = 0.0; nd.u = u_grav;
+    if (!__any_sync(0xffffffffu, active)) return;          // warp-uniform: nothing to evaluate (all done / skipped)
     Elements el_own = {0, 0, 0, 0, 0, 0};
     int ok = 0;
     if (active) ok = orbital_elements(u_grav, Ri, Vi, el_own) ? 1 : 0;
@@ -359,39 +362,57 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     el_oth.i = __shfl_xor_sync(0xffffffffu, el_own.i, 1); el_oth.omega = __shfl_xor_sync(0xffffffffu, el_own.omega, 1);
     el_oth.Omega = __shfl_xor_sync(0xffffffffu, el_own.Omega, 1); el_oth.f = __shfl_xor_sync(0xffffffffu, el_own.f, 1);
     const int ok_both = ok & __shfl_xor_sync(0xffffffffu, ok, 1);
-    nd.status = 0; nd.dvm = 0.0; nd.theta = 0.0; nd.f_cx = 0.0; nd.r_ft = 0.0;
-    nd.A0 = 0.0; nd.A1 = 0.0; nd.sth = 0.0; nd.cth = 1.0; nd.sq_e_sin = 0.0; nd.sq_k = 0.0; nd.r_c = 0.0; nd.u = u_grav;
+    const bool lane0 = craft == 0;
+    const Elements& c = lane0 ? el_own : el_oth;     // pursuer
+    const Elements& t = lane0 ? el_oth : el_own;     // target
+    // Quantities both nodes of an env share are evaluated ONCE per lane pair: the two lanes put different arguments
+    // through the same call and swap the results (every lane of the warp takes part in the shuffles; values of
+    // inactive lanes are never used).
+    // (1) sin/cos of the two inclinations: each lane its own craft's
+    const double2 sci = glibm::call::sincos(el_own.i);
+    const double si_x = __shfl_xor_sync(0xffffffffu, sci.x, 1), ci_x = __shfl_xor_sync(0xffffffffu, sci.y, 1);
+    const double si_c = lane0 ? sci.x : si_x, ci_c = lane0 ? sci.y : ci_x;
+    const double si_t = lane0 ? si_x : sci.x, ci_t = lane0 ? ci_x : sci.y;
+    // (2) lane 0: sin/cos of the pursuer's true anomaly; lane 1: of Omega_c - Omega_t
+    const double2 sc2 = glibm::call::sincos(lane0 ? c.f : c.Omega - t.Omega);
+    const double s2_x = __shfl_xor_sync(0xffffffffu, sc2.x, 1), c2_x = __shfl_xor_sync(0xffffffffu, sc2.y, 1);
+    const double sf0 = lane0 ? sc2.x : s2_x, cf0 = lane0 ? sc2.y : c2_x;
+    const double sdo = lane0 ? s2_x : sc2.x, cdo = lane0 ? c2_x : sc2.y;
+    // (3) calculate_latitudinal_angle, satellite_function.py:326-337: lane 0 -> temp1 / u_c1, lane 1 -> temp2 / u_t1.
+    // sin/cos of (Omega_t - Omega_c) = -(Omega_c - Omega_t) follow from the exact odd/even symmetry of __sin / __cos.
+    const double si_a = lane0 ? si_t : si_c, ci_a = lane0 ? ci_t : ci_c;
+    const double si_b = lane0 ? si_c : si_t, ci_b = lane0 ? ci_c : ci_t;
+    double temp = (si_a * (lane0 ? sdo : -sdo)) / (ci_a * si_b - si_a * ci_b * cdo);
+    const double temp_x = __shfl_xor_sync(0xffffffffu, temp, 1);
+    if (isnan(temp) || isnan(temp_x)) temp = 1.0;                        // :331-332 (both are replaced)
+    const double u_own = glibm::call::atan(temp);
+    const double u_x = __shfl_xor_sync(0xffffffffu, u_own, 1);
+    const double u_c1 = lane0 ? u_own : u_x, u_t1 = lane0 ? u_x : u_own;
+    // (4) squares (python `**`, i.e. libm pow): lane 0 -> e_c^2 and k^2, lane 1 -> e_t^2 and Delta_V_c^2
+    const double e2_own = glibm::call::pow2(el_own.e);
+    const double e2_x = __shfl_xor_sync(0xffffffffu, e2_own, 1);
+    const double e2_c = lane0 ? e2_own : e2_x, e2_t = lane0 ? e2_x : e2_own;
+    const double k = 1.0 + c.e * cf0;
+    const double dv = fuel_c;                                             // Delta_V_c (:328)
+    const double sq_own = glibm::call::pow2(lane0 ? k : dv);
+    const double sq_x = __shfl_xor_sync(0xffffffffu, sq_own, 1);
+    const double k2 = lane0 ? sq_own : sq_x, dv2 = lane0 ? sq_x : sq_own;
+    // ---- no shuffles below this line
     if (!active) return;
     if (!ok_both) { nd.status = -1; return; }
-    const Elements& c = craft == 0 ? el_own : el_oth;     // pursuer
-    const Elements& t = craft == 0 ? el_oth : el_own;     // target
-    // calculate_latitudinal_angle, satellite_function.py:326-337
-    double si_t, ci_t, si_c, ci_c, sdo, cdo, sdo2, cdo2;
-    glibm::sincos(t.i, &si_t, &ci_t); glibm::sincos(c.i, &si_c, &ci_c);
-    glibm::sincos(c.Omega - t.Omega, &sdo, &cdo);
-    sdo2 = -sdo; cdo2 = cdo;          // sin/cos of (Omega_t - Omega_c) = -(Omega_c - Omega_t): exact odd/even symmetry
-    double temp1 = (si_t * sdo) / (ci_t * si_c - si_t * ci_c * cdo);
-    double temp2 = (si_c * sdo2) / (ci_c * si_t - si_c * ci_t * cdo2);
-    if (isnan(temp1) || isnan(temp2)) { temp1 = 1.0; temp2 = 1.0; }      // :331-332
-    const double u_c1 = glibm::atan(temp1), u_t1 = glibm::atan(temp2);
     // :352-355; lane 0 -> node 1 (f_c1, r_ft1 uses f_t2), lane 1 -> node 2 (f_c2, r_ft2 uses f_t1) (Q5)
-    const double f_cx = (craft == 0 ? u_c1 : kPi + u_c1) - c.omega;
-    const double f_tx = (craft == 0 ? u_t1 + kPi : u_t1) - t.omega;
+    const double f_cx = (lane0 ? u_c1 : kPi + u_c1) - c.omega;
+    const double f_tx = (lane0 ? u_t1 + kPi : u_t1) - t.omega;
     nd.f_cx = f_cx;
-    nd.r_ft = (t.a * (1.0 - glibm::pow2(t.e))) / (1.0 + t.e * glibm::cos(f_tx));       // :363 / :365
-    const double one_m_e2 = 1.0 - glibm::pow2(c.e);
-    double sf0, cf0;
-    glibm::sincos(c.f, &sf0, &cf0);
-    const double k = 1.0 + c.e * cf0;
+    nd.r_ft = (t.a * (1.0 - e2_t)) / (1.0 + t.e * glibm::call::cos(f_tx));       // :363 / :365
+    const double one_m_e2 = 1.0 - e2_c;
     const double r_c = c.a * one_m_e2 / k;                                // :57
     const double p_c = c.a * one_m_e2;                                    // :58
-    const double dv = fuel_c;                                             // Delta_V_c (:328)
     // rf_extreme_point, satellite_function.py:462-494 with fai = 0
     const double df = f_cx - c.f;
-    double sdf, cdf;
-    glibm::sincos(df, &sdf, &cdf);
-    const double k2 = glibm::pow2(k), dv2 = glibm::pow2(dv);
-    const double tmp1 = glibm::pow2(sdf) / (u_grav * k2 / (p_c * dv2) - 1.0);   // :466 / :481
+    const double2 scdf = glibm::call::sincos(df);
+    const double sdf = scdf.x, cdf = scdf.y;
+    const double tmp1 = glibm::call::pow2(sdf) / (u_grav * k2 / (p_c * dv2) - 1.0);   // :466 / :481
     if (!(0.0 <= tmp1)) { nd.status = 1; return; }                                    // :478 -> (0, 0)
     // :469-470 with tan(fai) = 0: beta = atan(+-0 / sdf) = +-0 for every finite non-zero sdf, so cos(beta) = 1 and the
     // subtracted term u k^2 sin(beta)^2 / p_c is +-0 (u k^2 finite, p_c non-zero): dvm = sqrt(dv^2) bit for bit. The general
@@ -402,28 +423,27 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
         cb = 1.0;
         dvm = sqrt(dv2);
     } else {
-        const double beta = glibm::atan(0.0 / sdf);                                          // :469
-        double sb;
-        glibm::sincos(beta, &sb, &cb);
-        dvm = sqrt(dv2 - u_grav * k2 * glibm::pow2(sb) / p_c);                     // :470
+        const double2 scb = glibm::call::sincos(glibm::call::atan(0.0 / sdf));       // :469
+        cb = scb.y;
+        dvm = sqrt(dv2 - u_grav * k2 * glibm::call::pow2(scb.x) / p_c);               // :470
     }
     // :464, :473-476 (theta stays 0 outside both ranges, Q5). One acos for the warp, the range decides how it is used:
     // an if / else-if around two acos calls made every warp run the routine twice with part of its lanes.
-    const double ac = glibm::acos(cdf * 1.0);
+    const double ac = glibm::call::acos(cdf * 1.0);
     const bool in_a = (-kTwoPi <= df && df < -kPi) || (0.0 <= df && df < kPi);
     const bool in_b = (-kPi <= df && df < 0.0) || (kPi <= df && df < kTwoPi);
     const double theta = in_a ? ac : (in_b ? kTwoPi - ac : 0.0);
-    double sth, cth;
-    glibm::sincos(theta, &sth, &cth);
+    const double2 scth = glibm::call::sincos(theta);
+    const double sth = scth.x, cth = scth.y;
     const double sq = sqrt(u_grav / p_c);
     const double sq_e_sin = sq * c.e * sf0;                                           // :518 first term
     const double sq_k = sq * k * cb;                                                  // :519 first term
     nd.r_c = r_c; nd.sq_e_sin = sq_e_sin; nd.sq_k = sq_k; nd.dvm = dvm; nd.sth = sth; nd.cth = cth; nd.theta = theta;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        const double ag = (j == 0) ? kPi / 2 : -kPi / 2;                              // :516 / :534
-        double sg, cg;
-        glibm::sincos(ag, &sg, &cg);
+        // alpha_guess = +-pi/2 (:516 / :534): libm gives sin(+-pi/2) = +-1 and cos(+-pi/2) = 6.123233995736766e-17 (the double
+        // nearest pi/2 is below it); checked against glibm in tests/test_glibm_host.py
+        const double sg = (j == 0) ? 1.0 : -1.0, cg = 6.123233995736766e-17;
         const double v1x = sq_e_sin + dvm * cg;
         const double v1y = sq_k + dvm * sg;
         const double h = r_c * v1y;                                                   // :521
@@ -446,12 +466,12 @@ SAT_DEV double dz_guess(int j) { return (j == 0) ? kPi / 2 : -kPi / 2; }
 SAT_DEV bool dz_degenerate(double A, double sth, double dvm) { return A == 0.0 && sth == 0.0 && fabs(dvm) <= 1.7976931348623157e308; }
 
 SAT_DEV double dz_rf(const DzNode& nd, double alpha) {
-    double s, c;
-    glibm::sincos(alpha, &s, &c);
+    const double2 sc = glibm::call::sincos(alpha);
+    const double s = sc.x, c = sc.y;
     const double v1x = nd.sq_e_sin + nd.dvm * c;                                      // :525 / :541
     const double v1y = nd.sq_k + nd.dvm * s;                                          // :526 / :542
     const double hm = nd.r_c * v1y;
-    return fabs(glibm::pow2(hm) / (nd.u * (1.0 - nd.cth) + hm * v1y * nd.cth - hm * v1x * nd.sth));   // :530 / :545, :549-550
+    return fabs(glibm::call::pow2(hm) / (nd.u * (1.0 - nd.cth) + hm * v1y * nd.cth - hm * v1x * nd.sth));   // :530 / :545, :549-550
 }
 
 // returns 0/1/2, or -1 when the reference would raise; alpha0/alpha1 are ignored unless nd.status == 2
