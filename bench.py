@@ -9,10 +9,12 @@ substeps of both craft, terminal checks, danger-zone count, reward, observation/
 auto-reset) for every env of the batch, with the step's actions already resident in HBM (`value`) or
 arriving in host buffers through the reference-facing step(pa, ea) call (`e2e`). The same step with the
 two fused Gaussian actors sampling the actions on the device (config 3 "with fused actor sampling") is
-reported beside it as `full_step_with_actor_sampling`.
+reported beside it as `config3_full_step` (with its own roofline, the fp32 actor kernel).
 
 N = 1 workload: BASELINE config 3 (65 536 envs, S = 100 substeps of h = 1 s, J2 on). N > 1: the same
-per-GPU batch on every rank (weak scaling; envs are independent, no data-path collective).
+per-GPU batch on every rank (weak scaling; envs are independent, no data-path collective); in addition `config4`
+(1 048 576 envs / N per GPU, horizon-256 on-device rollout) and, at N = 8, the PPO section at config 5's
+2048-step horizon.
 
 One JSON line on stdout (rank 0). See DESIGN.md "Measurement" for every field.
 """
@@ -39,6 +41,21 @@ FLOP_ACTOR = 141824.0          # fp32 per actor forward
 # weight gradients 2 x 2 x (256 x 256 + 18 x 256) + heads  
 FLOP_PPO_SAMPLE_STEP = (141824.0 + 140800.0) + 2 * 131072.0 + 2 * 2 * (65536.0 + 4608.0) + 2 * 4 * 256.0
 BYTES_ENV_STEP = 345.0
+BYTES_GAE_SAMPLE = 17.0        # r 4 + v 4 + done 1 + adv 4 + v_target 4
+SM_COUNT, SM_GHZ = 148, 1.965
+FP64_NOMINAL_TFLOPS = SM_COUNT * 64 * 2 * SM_GHZ / 1e3      # 37.2: 64 DFMA lanes per SM
+FP32_NOMINAL_TFLOPS = SM_COUNT * 128 * 2 * SM_GHZ / 1e3     # 74.5: 128 FFMA lanes per SM
+
+
+def ncu_traffic(kernel, n_envs):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json: dram__bytes_read.sum +
+    dram__bytes_write.sum of one `ncu --set full` launch), scaled to this run's env count; the file names the capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(path))[kernel]
+    except Exception:
+        return None, "profiles/ncu_traffic.json has no entry for " + kernel
+    return rec["dram_bytes_per_launch"] * (n_envs / rec["envs"]), f"{rec['source']} ({rec['captured']}), {rec['envs']} envs, scaled by n"
 
 
 def parse():
@@ -58,8 +75,13 @@ def parse():
     ap.add_argument("--ppo-update", choices=("fused", "torch"), default="fused",
                     help="optimiser step: hand-written forward/backward/Adam kernels, or the PyTorch step (CUDA-graphed)")
     ap.add_argument("--cpu-sample-envs", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
+    ap.add_argument("--config4", action="store_true", help="also run BASELINE config 4 at N=1 (1 048 576 envs on one GPU); "
+                                                           "always run for N>1 (1 048 576 / N envs per GPU, T=256)")
+    ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()
     args.warmup_requested = args.warmup
+    if args.gpus >= 8 and "--ppo-horizon" not in " ".join(sys.argv):
+        args.ppo_horizon = 2048                  # config 5 proper: 2048-step x 65 536-env rollout on 8 GPUs (8192 envs/GPU)
     args.warmup = max(3, args.warmup)            # timing rule: never fewer than 3 untimed warm-up steps
     return args
 
@@ -150,13 +172,20 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "rk4_env_steps_per_sec", "value": value, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "envs_per_gpu": args.envs, "substeps": args.substeps,
-                       "note": "reference is pure Python and cannot travel to the GPU box; this arm times the CPU oracle "
-                               "port (C, OpenMP, literal restatement incl. MINPACK hybrd) of the same env step"},
+            "config": config_dict(args, None),
+            "note": "the reference is pure Python and cannot travel to the GPU box; this arm times the CPU oracle port (C, OpenMP, "
+                    "literal restatement incl. MINPACK hybrd) of the same env step on all host threads",
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": f"{n_envs} envs x {args.steps} steps (S={args.substeps} RK4+J2 substeps, env step only, actions given)"},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+def config_dict(args, value):
+    """the `config` object of the JSON line: identical keys (and values) in both arms so the driver can compare them"""
+    return {"workload": workload_name(args), "envs_per_gpu": args.envs, "substeps": args.substeps, "h": 1.0, "j2": True,
+            "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
+            "timing": "CUDA events per step on the launch stream, sum over steps, max over ranks (reference arm: wall clock per step)"}
 
 
 def workload_name(args):
@@ -223,6 +252,51 @@ def run_ppo_section(args, rank, world, dev, torch, dist, eng):
                 "(torch symmetric memory) in rank order after a device-side barrier; no NCCL call on the step"
                 if fused and agent._fused is not None and agent._fused.get("peers") else "NCCL, 2 flat buckets (286 KB + 284 KB) per step"),
             "timing": "wall clock with barrier + synchronize on both sides, max over ranks"}
+
+
+def run_config4(args, rank, world, dev, torch, dist, eng):
+    """BASELINE config 4: 1 048 576 envs split evenly over the ranks (524 288 / 262 144 / 131 072 per GPU), rk4 mode with J2,
+    S substeps, rollout horizon T = 256 with both actors sampling on the device and every transition stored (time-major
+    rollout buffer, 153 B/sample). Philox counters use the global env id, no collective. Device time, max over ranks."""
+    from ppo_rl_satellite_b200 import rollout
+    from ppo_rl_satellite_b200.dropin import ppo_continuous as P
+    total, T = 1 << 20, 256
+    lo, hi = rollout.shard_bounds(total, world, rank)
+    n = hi - lo
+    a = _PpoArgs(policy_dist="Gaussian", max_action=1.6, batch_size=T * n, mini_batch_size=65536, max_train_steps=int(3e6),
+                 lr_a=2e-4, lr_c=2e-4, gamma=0.99, lamda=0.95, epsilon=0.1, K_epochs=10, entropy_coef=0.01,
+                 set_adam_eps=True, use_grad_clip=True, use_lr_decay=True, use_adv_norm=True, state_dim=18, action_dim=3,
+                 hidden_width=256, use_tanh=True, use_orthogonal_init=True, chkpt_dir="/tmp")
+    torch.manual_seed(0)
+    env = eng.EnvBatch(n, mode="rk4", substeps=args.substeps, h=1.0, d_capture=20000.0, max_episode_steps=1000, device=dev)
+    rng = np.random.default_rng(4321 + rank)
+    env.set_state(np.array([200000.0, 0, 0]) + rng.normal(0, 3e4, (n, 3)), rng.normal(0, 3.0, (n, 3)),
+                  np.array([18000.0, 0, 0]) + rng.normal(0, 3e4, (n, 3)), rng.normal(0, 3.0, (n, 3)))
+    agent, opp = P.PPO_continuous(a, "pursuer", device=dev), P.PPO_continuous(a, "evader", device=dev)
+    tr = rollout.VectorTrainer(env, agent, opp, T, rank=0)
+    tr.row_offset = lo                                           # Philox counter = global env id (shard-invariant)
+    warm = rollout.VectorTrainer(env, agent, opp, 4, rank=0)
+    warm.row_offset = lo
+    warm.collect()
+    del warm
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); tr.collect(); e1.record(); e1.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    out = {"what": "1 048 576 envs / %d GPUs = %d envs per GPU, rk4 mode (S=%d, J2 on), T=256 on-device rollout: 2 actor samplings + env "
+                   "step per time step, transitions stored time-major; no collective; CUDA events around the rollout, max over ranks" % (world, n, args.substeps),
+           "envs_total": total, "envs_per_gpu": n, "horizon": T, "rollout_ms": ms, "ms_per_step": ms / T,
+           "env_steps_per_sec": total * T / (ms * 1e-3), "rk4_steps_per_sec": total * T / (ms * 1e-3) * 2 * args.substeps,
+           "episodes_finished": int(tr.buf.done.sum().item()), "err_envs": int(env.err.sum().item()),
+           "rollout_buffer_gb_per_gpu": tr.buf.bytes_per_sample * T * n / 1e9}
+    del tr, env, agent, opp
+    torch.cuda.empty_cache()
+    return out
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -398,6 +472,24 @@ def run_ours(args, rank, world, local_rank):
     xk1[0], xk1[1], xk1[2] = 7000 * torch.cos(ang), 7000 * torch.sin(ang), 100 * torch.randn(nk1, device=dev, dtype=torch.float64)
     xk1[3], xk1[4], xk1[5] = -7.5 * torch.sin(ang), 7.5 * torch.cos(ang), 0.1 * torch.randn(nk1, device=dev, dtype=torch.float64)
     t_k1, t_k1_min = time_kernel(lambda: eng.rk4_propagate(xk1, 1.0, 100))
+    # K4 + normalisation (HBM-bound, 17 B/sample): GAE reverse scan, advantage moments + normalise, running-stats update
+    def gae_case(T_, N_):
+        r_ = torch.randn((T_, N_), device=dev); v_ = torch.randn((T_ + 1, N_), device=dev)
+        d_ = (torch.rand((T_, N_), device=dev) < 0.02).to(torch.uint8)
+        a_ = torch.empty_like(r_); vt_ = torch.empty_like(r_)
+        ms, _ = time_kernel(lambda: eng.gae_time_major(r_, v_, d_, adv=a_, v_target=vt_), reps=5, warm=2)
+        ms_m, _ = time_kernel(lambda: eng.adv_moments(a_), reps=5, warm=2)
+        sums_ = eng.adv_moments(a_)
+        ms_n, _ = time_kernel(lambda: eng.adv_normalize_(a_, sums=sums_, group=False), reps=5, warm=2)
+        B_ = T_ * N_
+        return {"T": T_, "N": N_, "gae_ms": ms, "gae_gbs": BYTES_GAE_SAMPLE * B_ / (ms * 1e-3) / 1e9,
+                "adv_moments_ms": ms_m, "adv_moments_gbs": 4.0 * B_ / (ms_m * 1e-3) / 1e9,
+                "adv_normalize_ms": ms_n, "adv_normalize_gbs": 8.0 * B_ / (ms_n * 1e-3) / 1e9}
+    gae_cases = [gae_case(2048, 8192), gae_case(256, 65536)]
+    xs_norm = torch.randn((65536, 18), dtype=torch.float64, device=dev)
+    st_norm = eng.RunningStats(18, dev)
+    t_norm, _ = time_kernel(lambda: st_norm.update_normalize(xs_norm, out_dtype=torch.float32), reps=5, warm=2)
+    del xs_norm
     peak64 = eng.measure_vector_peak("fp64")
     peak32 = max(eng.measure_vector_peak("fp32"), eng.measure_vector_peak("fp32x2"))   # scalar FFMA vs packed FFMA2 chains
     ach_env = FLOP_ENV_STEP * (S / 100.0) * n / (t_env * 1e-3) / 1e12
@@ -428,6 +520,10 @@ def run_ours(args, rank, world, local_rank):
                       "moves it to the host on a second stream while the danger-zone kernel runs, reward/done are written to host "
                       "memory by that kernel; both streams are synchronised before the call returns; wall clock",
                "steps": ke, "rank_cpu_affinity": numa_cpus}
+    # ---------------- BASELINE config 4: 1 048 576 envs sharded over the ranks (J2 on), on-device rollout of horizon 256
+    config4 = None
+    if (world > 1 or args.config4) and not args.no_config4:
+        config4 = run_config4(args, rank, world, dev, torch, dist, eng)
     # ---------------- PPO samples/sec (BASELINE config 5 shape, per-GPU share): rollout + GAE + K-epoch update
     ppo = None
     if not args.no_ppo:
@@ -435,7 +531,8 @@ def run_ours(args, rank, world, local_rank):
         per_gpu_sample_steps = ppo["samples"] / world * 10
         ppo["optimizer_step_ms"] = 1e3 * ppo["update_s"] / ppo["optimizer_steps"]
         ppo["update_fp32_tflops_per_gpu"] = FLOP_PPO_SAMPLE_STEP * per_gpu_sample_steps / ppo["update_s"] / 1e12
-        ppo["update_frac_of_measured_fp32_peak"] = ppo["update_fp32_tflops_per_gpu"] / peak32
+        ppo["update_frac_of_nominal_fp32_peak"] = ppo["update_fp32_tflops_per_gpu"] / FP32_NOMINAL_TFLOPS
+        ppo["update_frac_of_measured_ffma_chain"] = ppo["update_fp32_tflops_per_gpu"] / peak32
         ppo["update_flops_per_sample_step"] = FLOP_PPO_SAMPLE_STEP
     clocks = sampler.stop() if rank == 0 else None     # sampled from warm-up to the end of every GPU-timed section
 
@@ -454,55 +551,79 @@ def run_ours(args, rank, world, local_rank):
                          f"CPU oracle port in C with OpenMP on all {cores} host threads, {dt:.1f} s"}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(peaks_path) else "fallback 6650 GB/s (B200_PROFILING.md)"
+    flop_step = FLOP_ENV_STEP * (S / 100.0)
+    ach_front = flop_step * n / (t_front * 1e-3) / 1e12
+    traffic_front, traffic_front_src = ncu_traffic("env_front_rk4_kernel", n)
+    traffic_finish, traffic_finish_src = ncu_traffic("env_step_kernel", n)
+    traffic_actor, traffic_actor_src = ncu_traffic("actor_kernel", n)
+    for c in gae_cases:
+        for k_ in ("gae", "adv_moments", "adv_normalize"):
+            c[k_ + "_frac_of_hbm_peak"] = c[k_ + "_gbs"] / hbm_peak
     line = {
         "metric": "rk4_env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "envs_per_gpu": n, "substeps": S, "h": 1.0, "j2": True,
-                   "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
-                   "timing": "CUDA events per step on the launch stream, sum over steps, max over ranks",
-                   "rk4_steps_per_sec": value * 2 * S},
+        "config": config_dict(args, value),
+        "rk4_steps_per_sec": value * 2 * S,
         "gpu_launches": LAUNCHES_PER_STEP * args.steps,
         "wall_s_timed_region": wall,
         "e2e": e2e,
+        # FP64 / FP32 vector peaks are not in MEASURED_PEAKS.json: `peak` is the nominal pipe rate (lanes x 2 x max SM clock);
+        # the FMA-chain microbenchmark of this run is reported beside it (frac_of_measured_chain)
         "roofline": {"kernel": "env_front_rk4_kernel: impulse + 2 x S RK4+J2 substeps of both craft = the dominant launch of the env step "
                                "and the one that performs all of the step's algorithmic (SURVEY s8d) FLOPs",
-                     "bound": "fp64", "achieved": FLOP_ENV_STEP * (S / 100.0) * n / (t_front * 1e-3) / 1e12, "peak": peak64,
-                     "unit": "TFLOP/s", "frac": FLOP_ENV_STEP * (S / 100.0) * n / (t_front * 1e-3) / 1e12 / peak64,
+                     "bound": "fp64", "achieved": ach_front, "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
+                     "frac": ach_front / FP64_NOMINAL_TFLOPS,
+                     "peak_source": "nominal FP64 pipe rate 148 SMs x 64 DFMA lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP64 entry)",
+                     "measured_dfma_chain_tflops": peak64, "frac_of_measured_chain": ach_front / peak64,
                      "launch_ms": t_front, "share_of_step": t_front / (t_front + t_finish + t_merge),
-                     "peak_nominal": 148 * 64 * 2 * 1.965e9 / 1e12,
-                     "frac_of_nominal": FLOP_ENV_STEP * (S / 100.0) * n / (t_front * 1e-3) / 1e12 / (148 * 64 * 2 * 1.965e9 / 1e12),
-                     "traffic": 9.97e6 * (n / 65536.0), "traffic_unit": "bytes per launch",
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of env_front_rk4_kernel at 65 536 envs "
-                                       "(profiles/r01_ncu_kernels.txt), scaled by n; algorithmic 224 B/env = 14.7 MB, the 9.4 MB state "
-                                       "stays L2-resident between steps",
-                     "peak_source": "DFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                     "algorithmic_flops_per_env_step": FLOP_ENV_STEP * (S / 100.0),
+                     "traffic": traffic_front, "traffic_unit": "bytes per launch", "traffic_source": traffic_front_src,
+                     "algorithmic_flops_per_env_step": flop_step, "algorithmic_bytes_per_env_step": BYTES_ENV_STEP,
                      "timing": "CUDA events recorded between the launches inside sat_env_step_timed, L2 flushed between iterations",
                      "whole_step": {"what": "front + finish (terminal checks, danger-zone root solves, reward, observations) + statistics "
                                             "merge, counting only the RK4 FLOPs as useful", "launch_ms": t_env, "launch_ms_min": t_env_min,
                                     "front_ms": t_front, "finish_ms": t_finish, "merge_ms": t_merge,
-                                    "achieved": ach_env, "frac": ach_env / peak64,
-                                    "traffic": 26.72e6 * (n / 65536.0),
+                                    "achieved": ach_env, "frac": ach_env / FP64_NOMINAL_TFLOPS,
+                                    "finish_kernel_traffic": traffic_finish, "finish_kernel_traffic_source": traffic_finish_src,
                                     "hbm_achieved_gbs": BYTES_ENV_STEP * n / (t_env * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak}},
+        # BASELINE config 3 exactly as worded ("full step ... with fused actor sampling"): both actors sample on the device, then the env step
+        "config3_full_step": {
+            "what": "pursuer + evader fused Gaussian actor kernels (observation rebuilt + normalised from the fp64 state, Philox "
+                    "sampling, CPPO_main.py:122-123) + the env step above (:132); 5 launches; CUDA events, L2 flushed between steps",
+            "ms_per_step": t_full, "ms_per_step_min": t_full_min, "per_gpu_env_steps_per_sec": n / (t_full * 1e-3),
+            "env_steps_per_sec": n * world / (t_full * 1e-3),
+            "split_ms": {"actor_x2": 2 * t_act, "env_front": t_front, "env_finish": t_finish, "stats_merge": t_merge},
+            "roofline": {"kernel": "actor_kernel<false> (fp32 FFMA2 register-tile MLP; 2 launches = %.0f %% of this step)" % (100 * 2 * t_act / t_full),
+                         "bound": "fp32", "achieved": ach_act, "peak": FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s",
+                         "frac": ach_act / FP32_NOMINAL_TFLOPS,
+                         "peak_source": "nominal FP32 pipe rate 148 SMs x 128 FFMA lanes x 2 x 1.965 GHz",
+                         "measured_ffma_chain_tflops": peak32, "frac_of_measured_chain": ach_act / peak32, "launch_ms": t_act,
+                         "traffic": traffic_actor, "traffic_source": traffic_actor_src},
+            "as_4_independent_shards_on_4_streams": None if t_full4 is None else {
+                "ms_per_step": t_full4, "per_gpu_env_steps_per_sec": n / (t_full4 * 1e-3),
+                "what": "the same work as 4 env shards with per-shard running statistics on 4 streams: the FP32 actor kernels of "
+                        "one shard overlap the FP64 env kernels of another"}},
+        "config4": config4,
         "kernels": {
             "rk4_kernel (K1, 2^20 states x 100 substeps, J2)": {"ms": t_k1, "bound": "fp64", "achieved_tflops": ach_k1,
-                                                              "frac_of_measured_fp64_peak": ach_k1 / peak64,
+                                                              "frac_of_nominal_fp64_peak": ach_k1 / FP64_NOMINAL_TFLOPS,
+                                                              "frac_of_measured_dfma_chain": ach_k1 / peak64,
                                                               "fp64_instr_per_rk4_step": FP64_INSTR_RK4_J2,
-                                                              "fp64_pipe_util_vs_measured_dfma_rate": (100 * nk1 / (t_k1 * 1e-3)) * FP64_INSTR_RK4_J2 / (peak64 * 1e12 / 2),
+                                                              "fp64_pipe_busy_implied": (100 * nk1 / (t_k1 * 1e-3)) * FP64_INSTR_RK4_J2 / (FP64_NOMINAL_TFLOPS * 1e12 / 2),
                                                               "rk4_steps_per_sec": 100 * nk1 / (t_k1 * 1e-3)},
             "actor_kernel (K3, one actor)": {"ms": t_act, "bound": "fp32", "achieved_tflops": ach_act,
-                                             "frac_of_measured_fp32_peak": ach_act / peak32},
+                                             "frac_of_nominal_fp32_peak": ach_act / FP32_NOMINAL_TFLOPS,
+                                             "frac_of_measured_ffma_chain": ach_act / peak32},
             "env_step_kernel<rk4> (K2)": {"ms": t_env, "env_steps_per_sec": n / (t_env * 1e-3)},
-            "measured_fp64_peak_tflops": peak64, "measured_fp32_peak_tflops": peak32},
-        "full_step_with_actor_sampling": {"ms_per_step": t_full, "env_steps_per_sec": n * world / (t_full * 1e-3) if world == 1 else None,
-                                          "per_gpu_env_steps_per_sec": n / (t_full * 1e-3),
-                                          "what": "pursuer + evader fused Gaussian actor kernels (obs rebuilt + normalised from the fp64 state, "
-                                                  "Philox sampling) + the env step above; 4 launches",
-                                          "as_4_independent_shards_on_4_streams": None if t_full4 is None else {
-                                              "ms_per_step": t_full4, "per_gpu_env_steps_per_sec": n / (t_full4 * 1e-3),
-                                              "what": "the same work as 4 env shards with per-shard running statistics on 4 streams: the FP32 "
-                                                      "actor kernels of one shard overlap the FP64 env kernels of another"}},
+            "gae + advantage normalisation (K4, bound hbm, 17 / 4 / 8 B per sample)": gae_cases,
+            "sat_norm_update (65536 x 18 fp64 -> running stats + fp32 normalised)": {
+                "ms": t_norm, "gbs": 65536 * 18 * (8 + 8 + 4) / (t_norm * 1e-3) / 1e9,
+                "frac_of_hbm_peak": 65536 * 18 * (8 + 8 + 4) / (t_norm * 1e-3) / 1e9 / hbm_peak,
+                "note": "4.7 MB per call: launch-latency bound (two passes + merge), not bandwidth bound"},
+            "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+            "nominal_fp64_peak_tflops": FP64_NOMINAL_TFLOPS, "nominal_fp32_peak_tflops": FP32_NOMINAL_TFLOPS,
+            "measured_dfma_chain_tflops": peak64, "measured_ffma_chain_tflops": peak32},
         "ppo": ppo,
         "cpu_baseline": cpu,
         "clocks": clocks,
