@@ -148,6 +148,111 @@ def cpu_env_steps_per_s(n_envs, steps, substeps, nthreads):
     return n_envs * steps / dt, dt
 
 
+def reference_python_rows():
+    """BASELINE.md s3 rows timed with the reference's OWN Python code (unmodified files staged in the git-ignored baseline/_ref
+    by tools/stage_reference.py) on this box's host cores: C-env-1, C-rk4-scalar, C-rk4-batch, C-actor, C-gae, C-update.
+    Bounded to ~2 s per row. Returns None when the staged reference is absent."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "environment.py")):
+        return None
+    import contextlib, io
+    os.environ["SAT_REFERENCE_DIR"] = ref
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import refshim
+        import torch
+        mods = refshim.load()
+        rows = {"source": "unmodified reference files in baseline/_ref (tools/stage_reference.py), python %s, numpy %s, torch %s, "
+                          "torch threads %d" % (sys.version.split()[0], np.__version__, torch.__version__, torch.get_num_threads())}
+        rng = np.random.default_rng(1)
+
+        def timed(fn, budget=2.0, min_iters=3):
+            n_, t0 = 0, time.perf_counter()
+            while True:
+                fn(); n_ += 1
+                dt = time.perf_counter() - t0
+                if n_ >= min_iters and dt >= budget:
+                    return n_ / dt, n_, dt
+        # C-env-1: env.step (Flag 0, CW propagation + danger zone + reward) as shipped, stdout suppressed, 1 core
+        env = refshim.make_env(20000, 1000)
+        env.reset(0)
+        cnt = [0]
+        def env_step():
+            cnt[0] += 1
+            _, _, d = refshim.quiet_step(env, rng.uniform(-2, 2, 3), rng.uniform(-2, 2, 3), cnt[0])
+            if d:
+                env.reset(0); cnt[0] = 0
+        for _ in range(50):
+            env_step()
+        rate, k, dt = timed(env_step)
+        rows["C-env-1"] = {"value": rate, "unit": "env-steps/s", "cores": 1, "sample": f"{k} reference env.step calls (cw mode as shipped), {dt:.1f} s",
+                           "code": "environment.py:81-179"}
+        # C-rk4-scalar / C-rk4-batch: the script's RungeKutta (lines 9-40 executed unmodified)
+        ns = refshim.load_rk4_script()
+        x1 = np.array([6678.137, 0.0, 0.0, 0.0, 6.789530297, 3.686414173])
+        st = {"x": x1}
+        def rk_scalar():
+            st["x"] = ns["RungeKutta"](0.0, st["x"], 1.0)
+        rate, k, dt = timed(rk_scalar, budget=1.5)
+        rows["C-rk4-scalar"] = {"value": rate, "unit": "RK4 steps/s", "cores": 1, "sample": f"{k} scalar RungeKutta calls, {dt:.1f} s",
+                                "code": "RK4 script :15-40"}
+        ang = rng.uniform(0, 2 * np.pi, 4096)
+        xb = np.array([7000 * np.cos(ang), 7000 * np.sin(ang), rng.uniform(-500, 500, 4096), -7.5 * np.sin(ang), 7.5 * np.cos(ang), rng.uniform(-.5, .5, 4096)])
+        stb = {"x": xb}
+        def rk_batch():
+            stb["x"] = ns["RungeKutta"](0.0, stb["x"], 1.0)
+        rate, k, dt = timed(rk_batch, budget=1.5)
+        rows["C-rk4-batch"] = {"value": rate * 4096, "unit": "RK4 steps/s", "cores": 1, "sample": f"{k} RungeKutta calls on a (6, 4096) array, {dt:.1f} s",
+                               "code": "RK4 script :15-40"}
+        # C-actor / C-gae / C-update: the reference's PPO_continuous
+        P = mods["ppo_continuous"]
+        a = _PpoArgs(policy_dist="Gaussian", max_action=1.6, batch_size=2048, mini_batch_size=64, max_train_steps=int(3e6),
+                     lr_a=2e-4, lr_c=2e-4, gamma=0.99, lamda=0.95, epsilon=0.1, K_epochs=10, entropy_coef=0.01, set_adam_eps=True,
+                     use_grad_clip=True, use_lr_decay=True, use_adv_norm=True, state_dim=18, action_dim=3, hidden_width=256,
+                     use_tanh=True, use_orthogonal_init=True, chkpt_dir="/tmp", max_episode_steps=1000)
+        with contextlib.redirect_stdout(io.StringIO()):
+            agent = P.PPO_continuous(a, "pursuer")
+        s1 = rng.normal(0, 1, 18)
+        rate, k, dt = timed(lambda: agent.choose_action(s1), budget=1.5)
+        rows["C-actor"] = {"value": rate, "unit": "choose_action calls/s (batch 1)", "cores": torch.get_num_threads(),
+                           "sample": f"{k} calls, {dt:.1f} s", "code": "ppo_continuous.py:176-189"}
+        xb_ = torch.randn(65536, 18)
+        with torch.no_grad():
+            rate, k, dt = timed(lambda: agent.actor(xb_), budget=1.5)
+        rows["C-actor-batch"] = {"value": rate * 65536, "unit": "actor forwards/s on a [65536, 18] tensor", "cores": torch.get_num_threads(),
+                                 "sample": f"{k} forwards, {dt:.1f} s", "code": "ppo_continuous.py:83-95"}
+        RB = mods["replaybuffer"].ReplayBuffer
+        rb = RB(a)
+        for i in range(2048):
+            rb.store(rng.normal(0, 1, 18), rng.uniform(-1, 1, 3), rng.normal(-1, .1, 3), rng.normal(), rng.normal(0, 1, 18), (i % 1000) == 999, (i % 1000) == 999)
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            agent.update(rb, 0)
+        dt = time.perf_counter() - t0
+        rows["C-update"] = {"value": 2048 / dt, "unit": "rollout samples/s through one update (2048 / 64 / K=10, GAE block included)",
+                            "cores": torch.get_num_threads(), "sample": f"1 update, {dt:.2f} s", "code": "ppo_continuous.py:191-242"}
+        # C-gae: the reference's GAE block alone (:198-210), exec'd on the same buffer
+        s_, a_, lp_, r_, sn_, dw_, dn_ = rb.numpy_to_tensor()
+        def gae_block():
+            adv, gae = [], 0
+            with torch.no_grad():
+                vs, vsn = agent.critic(s_), agent.critic(sn_)
+                deltas = r_ + a.gamma * (1.0 - dw_) * vsn - vs
+                for delta, d in zip(reversed(deltas.flatten().numpy()), reversed(dn_.flatten().numpy())):
+                    gae = delta + a.gamma * a.lamda * gae * (1.0 - d)
+                    adv.insert(0, gae)
+                adv = torch.tensor(adv, dtype=torch.float).view(-1, 1)
+                return adv + vs
+        rate, k, dt = timed(gae_block, budget=1.0)
+        rows["C-gae"] = {"value": rate * 2048, "unit": "samples/s", "cores": 1, "sample": f"{k} passes of the GAE block over 2048 samples, {dt:.1f} s",
+                         "code": "ppo_continuous.py:198-210"}
+        return rows
+    except Exception as e:                                   # a reported baseline must never break the GPU line
+        return {"error": repr(e)}
+    finally:
+        sys.path.remove(os.path.join(ROOT, "tests"))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -250,7 +355,7 @@ def run_ppo_section(args, rank, world, dev, torch, dist, eng):
             "cuda_graph": bool(not fused and use_graph and agent._graph is not None), "allreduce": None if world == 1 else (
                 "fused into the Adam kernel: every rank reads all ranks' flat gradients (286 KB + 284 KB) from NVLink peer memory "
                 "(torch symmetric memory) in rank order after a device-side barrier; no NCCL call on the step"
-                if fused and agent._fused is not None and agent._fused.get("peers") else "NCCL, 2 flat buckets (286 KB + 284 KB) per step"),
+                if fused and agent._fused is not None and any(agent._fused.get("peers", {}).values()) else "NCCL, 2 flat buckets (286 KB + 284 KB) per step"),
             "timing": "wall clock with barrier + synchronize on both sides, max over ranks"}
 
 
@@ -548,7 +653,10 @@ def run_ours(args, rank, world, local_rank):
         rate, dt = cpu_env_steps_per_s(n_cpu, k_cpu, S, cores)
         cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} envs x {k_cpu} steps of the same env step (S={S} RK4+J2 substeps both craft + danger zone + reward), "
-                         f"CPU oracle port in C with OpenMP on all {cores} host threads, {dt:.1f} s"}
+                         f"CPU oracle port in C with OpenMP on all {cores} host threads, {dt:.1f} s",
+               # kind "reference": the reference's own Python on this host; these are different, much slower
+               # workloads (single env, cw mode) and are reported beside the port, not used for the headline ratio
+               "reference_python": reference_python_rows()}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
     hbm_src = "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(peaks_path) else "fallback 6650 GB/s (B200_PROFILING.md)"

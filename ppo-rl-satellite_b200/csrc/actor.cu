@@ -243,11 +243,16 @@ inline int launch_status() {
 
 template <bool CRITIC, bool PAIR = false>
 int configure() {
-    static int done = 0;     // benign race: idempotent attribute set
-    if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(actor_kernel<CRITIC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    // the attribute is per device (per context): a process that samples on cuda:0 and then on cuda:1 needs it on both.
+    // One flag per device ordinal; benign race (idempotent attribute set).
+    static unsigned char done[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        e = cudaFuncSetAttribute(actor_kernel<CRITIC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return (int)e;
-        done = 1;
+        if (dev >= 0 && dev < 64) done[dev] = 1;
     }
     return SAT_OK;
 }

@@ -962,6 +962,17 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
     char* d_ws = base + 2 * al(n * 12) + al(n * 72) + al(n * 8) + al(n);
     SatEnvParams q = *p;
     q.action_dtype = SAT_ACT_F32;
+    // error exits after work was forked onto the second stream: join both streams and release the fork event first
+    cudaEvent_t fork = nullptr;
+    auto leave = [&](int code) {
+        if (fork) {
+            cudaStreamSynchronize(s0);
+            if (s1) cudaStreamSynchronize(s1);
+            cudaEventDestroy(fork);
+            fork = nullptr;
+        }
+        return code;
+    };
     if (chunks <= 0) {
         // zero-copy form: pinned (UVA-mapped) host buffers are handed to the kernels directly: the action reads and the
         // observation / reward / done stores cross PCIe from inside the kernels. With chunks < 0 the batch is additionally
@@ -985,11 +996,12 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
             // reward) runs; kernel B writes reward / done straight to host memory. Kernel B must not READ host memory
             // here: PCIe read requests may not pass the copy's posted writes, which stalled it by ~50 us.
             // Measured at 65 536 envs: 241 us/step (all zero-copy: 287; two zero-copy ranges: 266; staged: 306).
-            static thread_local cudaEvent_t front_ev[16] = {};
+            static thread_local cudaEvent_t front_ev[64] = {};   // one event per device ordinal (events belong to a device)
             int devid = 0;
-            cudaGetDevice(&devid);
-            cudaEvent_t& fe = front_ev[devid & 15];
             cudaError_t ce0;
+            if ((ce0 = cudaGetDevice(&devid)) != cudaSuccess) return (int)ce0;
+            if (devid < 0 || devid >= 64) return SAT_ERR_SIZE;
+            cudaEvent_t& fe = front_ev[devid];
             if (!fe && (ce0 = cudaEventCreateWithFlags(&fe, cudaEventDisableTiming)) != cudaSuccess) return (int)ce0;
             rc = env_step_impl(st, dev[0], dev[1], nullptr, nullptr, nullptr, nullptr, (double*)dev[3], (uint8_t*)dev[4],
                                nullptr, nullptr, nullptr, d_ws, &q, (void*)s0, nullptr, d_obs, fe, d_pa, d_ea);
@@ -1003,7 +1015,6 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
         if (ok) {
             const int64_t per = ((n + ranges - 1) / ranges + 63) / 64 * 64;
             const int64_t ws_per = sat_workspace_bytes(per);
-            cudaEvent_t fork = nullptr;
             cudaError_t ce0;
             if (ranges > 1) {
                 if ((ce0 = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return (int)ce0;
@@ -1017,14 +1028,11 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
                 rc = sat_env_step(&sub, (const float*)dev[0] + lo * 3, (const float*)dev[1] + lo * 3, nullptr,
                                   (float*)dev[2] + lo * 18, nullptr, nullptr, (double*)dev[3] + lo, (uint8_t*)dev[4] + lo,
                                   nullptr, nullptr, nullptr, d_ws + (int64_t)k * ws_per, &q, (void*)((k & 1) ? s1 : s0));
-                if (rc) return rc;
+                if (rc) return leave(rc);
             }
-            if ((ce0 = cudaStreamSynchronize(s0)) != cudaSuccess) return (int)ce0;
-            if (ranges > 1) {
-                if ((ce0 = cudaStreamSynchronize(s1)) != cudaSuccess) return (int)ce0;
-                cudaEventDestroy(fork);
-            }
-            return SAT_OK;
+            if ((ce0 = cudaStreamSynchronize(s0)) != cudaSuccess) return leave((int)ce0);
+            if (ranges > 1 && (ce0 = cudaStreamSynchronize(s1)) != cudaSuccess) return leave((int)ce0);
+            return leave(SAT_OK);
         }
         chunks = ranges;                                     // pageable memory: staged copies
     }
@@ -1033,7 +1041,6 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
     if (chunks < 1 || !s1) chunks = 1;
     int64_t per = ((n + chunks - 1) / chunks + 63) / 64 * 64;
     cudaError_t ce;
-    cudaEvent_t fork = nullptr;
     if (chunks > 1) {
         if ((ce = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return (int)ce;
         cudaEventRecord(fork, s0);
@@ -1045,21 +1052,18 @@ int sat_env_step_host(const SatEnvState* st, const float* pa_host, const float* 
         const int64_t m = (n - lo < per) ? n - lo : per;
         cudaStream_t s = (k & 1) ? s1 : s0;
         SatEnvState sub = {st->state + lo, st->istate + lo, m, st->ld};
-        if ((ce = cudaMemcpyAsync(d_pa + lo * 3, pa_host + lo * 3, m * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)ce;
-        if ((ce = cudaMemcpyAsync(d_ea + lo * 3, ea_host + lo * 3, m * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)ce;
+        if ((ce = cudaMemcpyAsync(d_pa + lo * 3, pa_host + lo * 3, m * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return leave((int)ce);
+        if ((ce = cudaMemcpyAsync(d_ea + lo * 3, ea_host + lo * 3, m * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return leave((int)ce);
         rc = sat_env_step(&sub, d_pa + lo * 3, d_ea + lo * 3, nullptr, d_obs + lo * 18, nullptr, nullptr, d_rew + lo,
                           d_done + lo, nullptr, nullptr, nullptr, d_ws + (int64_t)k * ws_per, &q, (void*)s);
-        if (rc) return rc;
-        if ((ce = cudaMemcpyAsync(obs_host + lo * 18, d_obs + lo * 18, m * 72, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
-        if ((ce = cudaMemcpyAsync(reward_host + lo, d_rew + lo, m * 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
-        if ((ce = cudaMemcpyAsync(done_host + lo, d_done + lo, m, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)ce;
+        if (rc) return leave(rc);
+        if ((ce = cudaMemcpyAsync(obs_host + lo * 18, d_obs + lo * 18, m * 72, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return leave((int)ce);
+        if ((ce = cudaMemcpyAsync(reward_host + lo, d_rew + lo, m * 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return leave((int)ce);
+        if ((ce = cudaMemcpyAsync(done_host + lo, d_done + lo, m, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return leave((int)ce);
     }
-    if ((ce = cudaStreamSynchronize(s0)) != cudaSuccess) return (int)ce;
-    if (chunks > 1) {
-        if ((ce = cudaStreamSynchronize(s1)) != cudaSuccess) return (int)ce;
-        cudaEventDestroy(fork);
-    }
-    return SAT_OK;
+    if ((ce = cudaStreamSynchronize(s0)) != cudaSuccess) return leave((int)ce);
+    if (chunks > 1 && (ce = cudaStreamSynchronize(s1)) != cudaSuccess) return leave((int)ce);
+    return leave(SAT_OK);
 }
 
 int sat_norm_update(double* stats, const double* x, int64_t n, int dim, int update,

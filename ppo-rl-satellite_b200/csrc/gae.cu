@@ -25,25 +25,93 @@ __device__ __forceinline__ float gae_step(float delta, float gl, float gae, floa
     return __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, gae), __fsub_rn(1.0f, d)));
 }
 
-__global__ void __launch_bounds__(128)
+// Time-major GAE, tiled: a CTA owns 32 adjacent envs (one 128-byte row segment per time step) and walks time in tiles of
+// kGaeTile steps from the end of the rollout. All 8 warps stream a tile in (r, v, done -> registers while the previous tile
+// is being scanned), stage it in shared memory and turn it into deltas; warp 0 then runs the strictly sequential recursion
+// for its 32 envs out of shared memory (3 dependent fp32 operations per step, rounded exactly like the reference's numpy
+// float32 scalars), and all warps write adv / v_target back with full-line stores. The loads of tile i-1 are in flight during
+// the scan of tile i, so the kernel is limited by HBM (17 B/sample), not by the length of one env's dependency chain -
+// the one-thread-per-env form reached 7 % of HBM at the config-5 shard (T = 2048, N = 8192: 64 CTAs, 2048 dependent steps).
+constexpr int kGaeTile = 64;      // time steps per tile
+constexpr int kGaeEnvs = 32;      // envs per CTA
+constexpr int kGaeThreads = 256;
+constexpr int kGaePer = kGaeTile * kGaeEnvs / kGaeThreads;   // elements per thread per tile
+
+__global__ void __launch_bounds__(kGaeThreads)
 gae_time_major_kernel(const float* __restrict__ r, const float* __restrict__ v, const uint8_t* __restrict__ done,
                       const float* __restrict__ r_scale, int64_t T, int64_t N, float gamma, float gl,
                       float* __restrict__ adv, float* __restrict__ vt) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float gae = 0.0f;
-    float vnext = v[T * N + n];
-    for (int64_t t = T - 1; t >= 0; --t) {
-        const int64_t i = t * N + n;
-        const float d = done[i] ? 1.0f : 0.0f;
-        float rr = r[i];
-        if (r_scale) rr = __fmul_rn(rr, r_scale[t]);
-        const float vs = v[i];
-        const float delta = gae_delta(rr, gamma, d, vnext, vs);
-        gae = gae_step(delta, gl, gae, d);
-        adv[i] = gae;
-        vt[i] = __fadd_rn(gae, vs);                          // :208
-        vnext = vs;
+    __shared__ float s_x[kGaeTile][kGaeEnvs];      // reward, then delta, then gae
+    __shared__ float s_v[kGaeTile][kGaeEnvs];      // vs
+    __shared__ float s_d[kGaeTile][kGaeEnvs];      // done as 0 / 1
+    __shared__ float s_vtop[kGaeEnvs];             // v of the row above the tile (t + 1 of its last step)
+    __shared__ float s_gae[kGaeEnvs];              // recursion carry
+    const int lane_e = threadIdx.x & (kGaeEnvs - 1);
+    const int row0 = threadIdx.x / kGaeEnvs;       // 0..7: the thread handles rows row0, row0 + 8, ...
+    const int64_t e = (int64_t)blockIdx.x * kGaeEnvs + lane_e;
+    const bool ev = e < N;
+    if (threadIdx.x < kGaeEnvs) { s_gae[threadIdx.x] = 0.0f; s_vtop[threadIdx.x] = ev ? v[T * N + e] : 0.0f; }
+    float pr[kGaePer], pv[kGaePer], pd[kGaePer];
+    // tiles cover [lo, lo + len), processed from the end of the rollout; the first (topmost) tile may be partial
+    int64_t hi = T;
+    int64_t lo = ((T - 1) / kGaeTile) * kGaeTile;
+    auto prefetch = [&](int64_t lo_, int len_) {
+#pragma unroll
+        for (int k = 0; k < kGaePer; ++k) {
+            const int row = row0 + k * (kGaeThreads / kGaeEnvs);
+            if (row < len_ && ev) {
+                const int64_t i = (lo_ + row) * N + e;
+                float rr = r[i];
+                if (r_scale) rr = __fmul_rn(rr, r_scale[lo_ + row]);
+                pr[k] = rr; pv[k] = v[i]; pd[k] = done[i] ? 1.0f : 0.0f;
+            } else { pr[k] = 0.0f; pv[k] = 0.0f; pd[k] = 0.0f; }
+        }
+    };
+    prefetch(lo, (int)(hi - lo));
+    while (hi > 0) {
+        const int len = (int)(hi - lo);
+        __syncthreads();                            // previous tile fully written out; s_vtop / s_gae visible
+#pragma unroll
+        for (int k = 0; k < kGaePer; ++k) {
+            const int row = row0 + k * (kGaeThreads / kGaeEnvs);
+            s_x[row][lane_e] = pr[k]; s_v[row][lane_e] = pv[k]; s_d[row][lane_e] = pd[k];
+        }
+        const int64_t nlo = lo - kGaeTile;
+        if (lo > 0) prefetch(nlo, kGaeTile);        // next tile's loads fly during the delta pass and the scan
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kGaePer; ++k) {
+            const int row = row0 + k * (kGaeThreads / kGaeEnvs);
+            if (row < len) {
+                const float vnext = (row == len - 1) ? s_vtop[lane_e] : s_v[row + 1][lane_e];
+                s_x[row][lane_e] = gae_delta(s_x[row][lane_e], gamma, s_d[row][lane_e], vnext, s_v[row][lane_e]);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kGaeEnvs) {
+            float gae = s_gae[lane_e];
+#pragma unroll 8
+            for (int row = len - 1; row >= 0; --row) {
+                gae = gae_step(s_x[row][lane_e], gl, gae, s_d[row][lane_e]);
+                s_x[row][lane_e] = gae;
+            }
+            s_gae[lane_e] = gae;
+        }
+        __syncthreads();
+        if (ev) {
+#pragma unroll
+            for (int k = 0; k < kGaePer; ++k) {
+                const int row = row0 + k * (kGaeThreads / kGaeEnvs);
+                if (row < len) {
+                    const int64_t i = (lo + row) * N + e;
+                    const float g = s_x[row][lane_e];
+                    adv[i] = g;
+                    vt[i] = __fadd_rn(g, s_v[row][lane_e]);                  // :208
+                }
+            }
+        }
+        if (threadIdx.x < kGaeEnvs) s_vtop[lane_e] = s_v[0][lane_e];         // v[lo] is v(t + 1) for the tile below
+        hi = lo; lo = nlo;
     }
 }
 
@@ -95,9 +163,25 @@ __global__ void __launch_bounds__(kMomThreads)
 moments_partial_kernel(const float* __restrict__ x, int64_t count, double* __restrict__ partial) {
     __shared__ double s_sum[kMomThreads / 32], s_sq[kMomThreads / 32];
     double sum = 0.0, sq = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * kMomThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kMomThreads) {
-        const double v = (double)x[i];
-        sum += v; sq += v * v;
+    // four independent 128-bit loads in flight per thread; per-thread accumulation order is fixed -> deterministic
+    const int64_t stride = (int64_t)gridDim.x * kMomThreads;
+    const int64_t tid = (int64_t)blockIdx.x * kMomThreads + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const int64_t n4 = count >> 2;
+        for (int64_t i = tid; i < n4; i += 4 * stride) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = (i + u * stride < n4) ? x4[i + u * stride] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double a = q[u].x, b = q[u].y, c = q[u].z, d = q[u].w;
+                sum += (a + b) + (c + d); sq += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+        for (int64_t i = (n4 << 2) + tid; i < count; i += stride) { const double v = (double)x[i]; sum += v; sq += v * v; }
+    } else {
+        for (int64_t i = tid; i < count; i += stride) { const double v = (double)x[i]; sum += v; sq += v * v; }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -121,22 +205,34 @@ __global__ void moments_final_kernel(const double* __restrict__ partial, int nbl
     }
 }
 
-__global__ void adv_normalize_kernel(float* __restrict__ adv, int64_t count, const double* __restrict__ sums) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+__global__ void __launch_bounds__(256)
+adv_normalize_kernel(float* __restrict__ adv, int64_t count, const double* __restrict__ sums) {
     const double n = sums[2];
     const double mean = sums[0] / n;
     double var = (sums[1] - n * mean * mean) / (n - 1.0);      // torch.std(): unbiased
     if (var < 0.0) var = 0.0;
-    const float m = (float)mean, sd = (float)sqrt(var);
-    adv[i] = __fdiv_rn(__fsub_rn(adv[i], m), __fadd_rn(sd, 1e-5f));   // ppo_continuous.py:210
+    const float m = (float)mean, den = __fadd_rn((float)sqrt(var), 1e-5f);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(adv) & 15) == 0) {
+        float4* a4 = reinterpret_cast<float4*>(adv);
+        const int64_t n4 = count >> 2;
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 q = a4[i];
+            q.x = __fdiv_rn(__fsub_rn(q.x, m), den); q.y = __fdiv_rn(__fsub_rn(q.y, m), den);       // ppo_continuous.py:210
+            q.z = __fdiv_rn(__fsub_rn(q.z, m), den); q.w = __fdiv_rn(__fsub_rn(q.w, m), den);
+            a4[i] = q;
+        }
+        for (int64_t i = (n4 << 2) + tid; i < count; i += stride) adv[i] = __fdiv_rn(__fsub_rn(adv[i], m), den);
+    } else {
+        for (int64_t i = tid; i < count; i += stride) adv[i] = __fdiv_rn(__fsub_rn(adv[i], m), den);
+    }
 }
 
 inline int launch_status() {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SAT_OK : (int)e;
 }
-constexpr int kMomBlocks = 296;   // 2 per SM
+constexpr int kMomBlocks = 148 * 8;   // 8 per SM
 
 }  // namespace
 
@@ -147,8 +243,8 @@ int sat_gae(const float* r, const float* v, const uint8_t* done, const float* r_
     if (!r || !v || !done || !adv || !v_target) return SAT_ERR_NULL;
     if (T <= 0 || N <= 0) return SAT_ERR_SIZE;
     const float gl = (float)((double)gamma * (double)lamda);   // python float product, weak-cast to fp32
-    const unsigned blocks = (unsigned)((N + 127) / 128);
-    gae_time_major_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(r, v, done, r_scale, T, N, gamma, gl, adv, v_target);
+    const unsigned blocks = (unsigned)((N + kGaeEnvs - 1) / kGaeEnvs);
+    gae_time_major_kernel<<<blocks, kGaeThreads, 0, (cudaStream_t)stream>>>(r, v, done, r_scale, T, N, gamma, gl, adv, v_target);
     return launch_status();
 }
 
@@ -177,7 +273,10 @@ int sat_adv_moments(const float* adv, int64_t count, double* sums, void* workspa
 int sat_adv_normalize(float* adv, int64_t count, const double* sums, void* stream) {
     if (!adv || !sums) return SAT_ERR_NULL;
     if (count <= 0) return SAT_ERR_SIZE;
-    adv_normalize_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(adv, count, sums);
+    int64_t nb = (count / 4 + 255) / 256;
+    if (nb < 1) nb = 1;
+    if (nb > 148 * 16) nb = 148 * 16;
+    adv_normalize_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(adv, count, sums);
     return launch_status();
 }
 

@@ -166,22 +166,47 @@ class PPO_continuous:
 
     def _peer_allreduce(self, f, group):
         """True when the gradient all-reduce runs inside the Adam kernel over NVLink peer memory (NCCL process group on
-        CUDA, torch symmetric memory available, SAT_PEER_ALLREDUCE != 0); otherwise the step calls dist.all_reduce."""
-        if "peers" not in f:
+        CUDA, torch symmetric memory available, SAT_PEER_ALLREDUCE != 0); otherwise the step calls dist.all_reduce.
+        The decision is collective: a rank whose rendezvous failed would otherwise take the NCCL path while its peers wait in
+        the symmetric-memory barrier, so the local outcome is MIN-reduced over the group before anyone commits. Cached per
+        process group."""
+        cache = f.setdefault("peers", {})
+        key = id(group) if group is not None else None
+        if key not in cache:
             dist = torch.distributed
             ok = os.environ.get("SAT_PEER_ALLREDUCE", "1") != "0" and dist.get_backend(group) == "nccl"
+            err = None
             if ok:
                 try:
                     for n in f["nets"]:
                         n.enable_peer_allreduce(group)
-                except Exception as exc:          # no peer access / symmetric memory on this system: NCCL path
+                except Exception as exc:          # no peer access / symmetric memory on this system
+                    ok, err = False, exc
+            if dist.get_backend(group) == "nccl":
+                flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                all_ok = bool(flag.item())
+            else:
+                all_ok = ok
+            if not all_ok:
+                for n in f["nets"]:
+                    n.disable_peer_allreduce()     # private gradient buffer again on every rank
+                if err is not None or ok:
                     import warnings
-                    warnings.warn(f"symmetric-memory gradient exchange unavailable ({exc!r}); using NCCL all-reduce")
-                    ok = False
-                    for n in f["nets"]:
-                        n._peer = None
-            f["peers"] = ok
-        return f["peers"]
+                    warnings.warn(f"symmetric-memory gradient exchange unavailable on at least one rank ({err!r}); using NCCL all-reduce")
+            cache[key] = all_ok
+        return cache[key]
+
+    @staticmethod
+    def _require_equal_batches(B, group, device):
+        """Every rank must bring the same number of samples: the ranks issue one gradient exchange per minibatch, so
+        different ceil(B / mb) would dead-lock, and the exchange averages per-rank means with equal weights. Collective."""
+        dist = torch.distributed
+        t = torch.tensor([B, -B], dtype=torch.int64, device=device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        if int(t[0]) != -int(t[1]):
+            raise ValueError(f"PPO update with unequal per-rank batches (min {-int(t[1])}, max {int(t[0])} samples): shard the envs "
+                             f"evenly (n_total % world == 0) or trim the rollout to a common size")
 
     def _optimize_fused(self, s, a, a_logprob, adv, v_target, mb, group):
         """The actor chain and the critic chain are independent (ppo_continuous.py:216-239 shares only s[index]), so each
@@ -196,6 +221,7 @@ class PPO_continuous:
         na, nc = f["nets"]
         peers = False
         if world > 1:
+            self._require_equal_batches(B, group, self.device)
             peers = self._peer_allreduce(f, group)
         s, a, a_logprob = s.contiguous(), a.contiguous(), a_logprob.contiguous()
         adv, v_target = adv.reshape(-1).contiguous(), v_target.reshape(-1).contiguous()
@@ -327,6 +353,9 @@ class PPO_continuous:
         mb = mini_batch_size or self.mini_batch_size
         if fused:
             return self._optimize_fused(s, a, a_logprob, adv, v_target, mb, group)
+        dist = torch.distributed
+        if group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            self._require_equal_batches(B, group, self.device)
         tensors = (s, a, a_logprob, adv, v_target)
         graph = None
         if use_graph and B >= mb:

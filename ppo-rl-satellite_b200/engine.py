@@ -531,6 +531,7 @@ class PpoFusedNet:
         self.device = dev
         self.params = torch.zeros(self.n + 2, dtype=torch.float32, device=dev)
         self.grads = torch.zeros(self.n + 2, dtype=torch.float32, device=dev)        # [n] = minibatch loss
+        self._own_grads = self.grads
         self.exp_avg = torch.zeros(self.n + 2, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.n + 2, dtype=torch.float32, device=dev)
         self.step = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -562,6 +563,15 @@ class PpoFusedNet:
         if self.net is not None:
             self.net.grads = self.grads.data_ptr()
         hdl.barrier()
+        return self
+
+    def disable_peer_allreduce(self):
+        """back to a private gradient buffer (used when the symmetric-memory rendezvous did not succeed on EVERY rank)"""
+        if self._peer is not None or self.grads.data_ptr() != self._own_grads.data_ptr():
+            self._peer = None
+            self.grads = self._own_grads
+            if self.net is not None:
+                self.net.grads = self.grads.data_ptr()
         return self
 
     def _slices(self):

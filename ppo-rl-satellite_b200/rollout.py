@@ -38,8 +38,9 @@ class VectorTrainer:
     """Drives `agent` (learner: pursuer for flag 0, evader for flag 1) against `opponent` on an EnvBatch."""
 
     def __init__(self, env: eng.EnvBatch, agent, opponent, T: int, use_state_norm=True, use_reward_scaling=True,
-                 rank: int = 0, seed: int = 0):
+                 rank: int = 0, seed: int = 0, strict_errors: bool = False):
         self.env, self.agent, self.opponent, self.T = env, agent, opponent, T
+        self.strict_errors = strict_errors
         self.buf = RolloutBuffer(T, env.n, env.device)
         self.obs_stats = eng.RunningStats(18, env.device) if use_state_norm else None
         self.ret_stats = eng.RunningStats(1, env.device) if use_reward_scaling else None
@@ -67,6 +68,15 @@ class VectorTrainer:
             env.step(pa, ea, reward=buf.rew64[t], done=buf.done[t], obs_stats=self.obs_stats, ret_stats=self.ret_stats,
                      ret_std_out=buf.ret_std[t:t + 1] if self.ret_stats is not None else None)
             self.t_global += 1
+        # The reference raises where an element set is circular / parabolic (satellite_function.py:40-42 via :52-58); the
+        # kernel flags the env (err = 1, dz = 0) and goes on. One reduced flag per collect() makes that visible.
+        n_err = int(env.err.sum().item())
+        if n_err:
+            msg = f"{n_err} env(s) hit an element set for which the reference's danger-zone code raises (env.err); their rewards used dz = 0"
+            if self.strict_errors:
+                raise eng.L.SatError(msg)
+            import warnings
+            warnings.warn(msg)
         # observation after the last step (bootstrap value), normalised with the current statistics
         x = env.observe()
         if self.obs_stats is not None:

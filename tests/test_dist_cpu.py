@@ -55,6 +55,15 @@ def _worker(rank, world, port, q):
         mean = sums[0] / n
         var = (sums[1] - n * mean * mean) / (n - 1)
         ok = ok and abs(mean - full.mean()) < 1e-12 and abs(var.sqrt() - full.std()) < 1e-10
+        # per-rank batch sizes must agree before a PPO update (one gradient exchange per minibatch: unequal ceil(B / mb)
+        # would dead-lock): equal sizes pass, unequal sizes raise on EVERY rank (collective check)
+        from ppo_continuous import PPO_continuous
+        PPO_continuous._require_equal_batches(4096, None, "cpu")
+        try:
+            PPO_continuous._require_equal_batches(4096 + rank, None, "cpu")
+            ok = False
+        except ValueError as e:
+            ok = ok and "unequal per-rank batches" in str(e)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -212,3 +212,70 @@ def test_two_ranks_average_gradients_like_one_rank_on_the_union():
     assert np.abs(res[0] - one).max() <= 3e-5 and np.abs(res[0] - one).mean() <= 2e-6
     assert np.abs(one - torch.cat([p.detach().reshape(-1) for p in list(_pair(args)[0].actor.parameters())
                                    + list(_pair(args)[0].critic.parameters())]).cpu().numpy()).mean() > 1e-4
+
+
+def _nccl_peer_worker(rank, world, port, q):
+    import os, sys
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SAT_PEER_ALLREDUCE="1")
+    import torch.distributed as dist
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from ppo_rl_satellite_b200.dropin import ppo_continuous as P
+        args = _args(K=3, mb=512, B=512)
+        torch.manual_seed(0)
+        agent = P.PPO_continuous(args, "pursuer", device=dev)
+        with torch.no_grad():
+            agent.actor.mean_layer.weight.mul_(30.0)
+            agent.actor.log_std.copy_(torch.tensor([[-0.3, 0.1, 0.2]], device=dev))
+        g = torch.Generator(device=dev).manual_seed(1)                 # same 1024 rows on both ranks; each trains on its half
+        s = torch.randn(1024, 18, device=dev, generator=g)
+        with torch.no_grad():
+            d_ = agent.actor.get_dist(s)
+            act = torch.clamp(d_.mean + d_.stddev * torch.randn(1024, 3, device=dev, generator=g), -1.6, 1.6)
+            logp = d_.log_prob(act) + 0.06 * torch.randn(1024, 3, device=dev, generator=g)
+        adv = torch.randn(1024, 1, device=dev, generator=g); vt = torch.randn(1024, 1, device=dev, generator=g)
+        lo = rank * 512
+        agent.optimize(s[lo:lo + 512], act[lo:lo + 512], logp[lo:lo + 512], adv[lo:lo + 512], vt[lo:lo + 512], mini_batch_size=512, fused=True)
+        torch.cuda.synchronize()
+        peers = any(agent._fused["peers"].values())
+        flat = torch.cat([p.detach().reshape(-1) for p in list(agent.actor.parameters()) + list(agent.critic.parameters())])
+        # unequal per-rank batches must be refused on every rank instead of dead-locking
+        refused = False
+        try:
+            agent.optimize(s[:512 - 64 * rank], act[:512 - 64 * rank], logp[:512 - 64 * rank], adv[:512 - 64 * rank],
+                           vt[:512 - 64 * rank], mini_batch_size=128, fused=True)
+        except ValueError:
+            refused = True
+        q.put((rank, flat.cpu().numpy(), peers, refused))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gpus_nccl_peer_memory_gradient_exchange():
+    """2 GPUs, NCCL process group: the gradient exchange fused into the Adam kernel over NVLink peer memory
+    (sat_ppo_adam_peers, torch symmetric memory) gives bit-identical replicas that match one rank on the union batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_nccl_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (f, pe, rf) for r, f, pe, rf in (q.get(timeout=240) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] and res[1][1], "the peer-memory path was not taken"
+    assert res[0][2] and res[1][2], "unequal per-rank batches were not refused"
+    assert np.array_equal(res[0][0], res[1][0])
+    args = _args(K=3, mb=1024, B=1024)
+    agent, _ = _pair(args)
+    s, act, logp, adv, vt = _data(agent, 1024)
+    agent.optimize(s, act, logp, adv, vt, mini_batch_size=1024, fused=True)
+    one = torch.cat([p.detach().reshape(-1) for p in list(agent.actor.parameters()) + list(agent.critic.parameters())]).cpu().numpy()
+    assert np.abs(res[0][0] - one).max() <= 3e-5
