@@ -19,6 +19,7 @@ ICOL_DZ, ICOL_COUNT, ICOL_INTSTATE, ICOL_ERR = 0, 1, 2, 3
 MODE_CW, MODE_RK4 = 0, 1
 ACT_F32, ACT_F64 = 0, 1
 ACTOR_PACKED_FLOATS = 18 * 256 + 256 + 256 * 256 + 256 + 4 * 256 + 4 + 4
+ACTOR_TC_IMAGE_FLOATS = 2 * 256 * 256
 
 
 class SatEnvState(C.Structure):
@@ -93,6 +94,8 @@ SIGNATURES = {
     "sat_actor_pack": (C.c_int, [C.POINTER(SatActorWeights), _P, _P]),
     "sat_actor_sample": (C.c_int, [C.POINTER(SatActorWeights), _P, C.POINTER(SatEnvState), _P, _I64, _I64,
                                    _U64, _U64, _P, _P, _P, _P, _P, _P, _P]),
+    "sat_actor_sample_tc": (C.c_int, [C.POINTER(SatActorWeights), _P, _P, C.POINTER(SatEnvState), _P, _I64, _I64,
+                                      _U64, _U64, _P, _P, _P, _P, _P, _P, _P]),
     "sat_critic_forward": (C.c_int, [C.POINTER(SatActorWeights), _P, _I64, _P, _P]),
     "sat_actor_sample_pair": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P]),
     "sat_gae": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _F, _F, _P, _P, _P]),

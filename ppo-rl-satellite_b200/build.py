@@ -29,6 +29,7 @@ UNITS = {
     "cw_ode.cu": ["-fmad=false"],
     "reach.cu": ["-fmad=false"],
     "actor.cu": [],
+    "actor_tc.cu": [],
     "ppo_update.cu": [],
     "capi.cu": [],
 }

@@ -7,6 +7,7 @@ fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -426,6 +427,8 @@ class GaussianActorKernel:
         self.use_tanh = int(bool(use_tanh))
         self._keep = None
         self.w = None
+        self.use_tc = os.environ.get("SAT_ACTOR_TC", "0") == "1"      # hidden layer on the tensor cores (3xTF32)
+        self._tc_image = None
 
     def load_state_dict(self, sd):
         """sd: torch state_dict (or dict of arrays) with the reference's parameter names."""
@@ -452,8 +455,9 @@ class GaussianActorKernel:
 
     def sample(self, obs=None, env: EnvBatch | None = None, obs_stats: RunningStats | None = None, seed: int = 0,
                step: int = 0, row_offset: int = 0, eps_in=None, act=None, logp=None, mean_out=None, eps_out=None,
-               obs_out=None):
-        """obs: CUDA fp32 [n,18]; or env=EnvBatch to read (and optionally normalise) the state directly."""
+               obs_out=None, tc: bool | None = None):
+        """obs: CUDA fp32 [n,18]; or env=EnvBatch to read (and optionally normalise) the state directly.
+        tc: run the hidden layer as 3xTF32 on the tensor cores (sat_actor_sample_tc); default = self.use_tc."""
         torch = self.torch
         L.guard_device(self.device)
         if self.w is None:
@@ -461,6 +465,16 @@ class GaussianActorKernel:
         n = obs.shape[0] if obs is not None else env.n
         act = torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device) if act is None else act
         logp = torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device) if logp is None else logp
+        if (self.use_tc if tc is None else tc) and not self.critic:
+            if self._tc_image is None:
+                self._tc_image = torch.empty(L.ACTOR_TC_IMAGE_FLOATS, dtype=torch.float32, device=self.device)
+            L.check(self.lib.sat_actor_sample_tc(C.byref(self.w), self._tc_image.data_ptr(), L.ptr(obs),
+                                                 C.byref(env.st) if env is not None else None,
+                                                 L.ptr(obs_stats.buf) if obs_stats is not None else None, n,
+                                                 int(row_offset), int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1),
+                                                 L.ptr(eps_in), L.ptr(act), L.ptr(logp), L.ptr(mean_out), L.ptr(eps_out),
+                                                 L.ptr(obs_out), L.stream_ptr()), "sat_actor_sample_tc")
+            return act, logp
         L.check(self.lib.sat_actor_sample(C.byref(self.w), L.ptr(obs), C.byref(env.st) if env is not None else None,
                                           L.ptr(obs_stats.buf) if obs_stats is not None else None, n,
                                           int(row_offset), int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1),
