@@ -458,7 +458,7 @@ static double step_impulse(orc_env* e, const double pa_in[3], const double ea_in
     for (k = 0; k < 3; ++k) { pa[k] = clip16(pa_in[k]); ea[k] = clip16(ea_in[k]); }      /* :86-87 */
     for (k = 0; k < 3; ++k) d[k] = e->P[k] - e->E[k];
     dis_prev = orc_norm3(d);                                                             /* :89 */
-    if (e->flag == 0) {
+    if (e->flag == 0 || e->flag == 2) {                                                  /* Flag 2: :265-277, same gating */
         if (e->dis < e->d_range && e->dangerous_zone != 0) {                             /* :91-96 */
             add_dv(e, e->Ev, ea);
             if (e->int_state) { for (k = 0; k < 3; ++k) e->Pv[k] = trunc(e->Pv[k] + 0); }
@@ -482,6 +482,11 @@ static int step_finish(orc_env* e, double dis_prev, const double pa[3], int epis
     for (k = 0; k < 3; ++k) d[k] = e->P[k] - e->E[k];
     e->dis = orc_norm3(d);                                                               /* :132 */
     make_obs(e, obs);
+    if (e->flag == 2) {                                  /* :303-316: reward 0, danger zone not re-evaluated; the surrogate
+                                                            fit between (:295-301) is outside the hot path */
+        *reward = 0.0;
+        return (e->dis <= e->d_capture || episode_count >= e->max_episode_steps) ? 1 : 0;
+    }
     if (e->dis <= e->d_capture) { *reward = (e->flag == 0) ? 100.0 : -150.0; return 1; } /* :139-142 / :221-225 */
     if (episode_count >= e->max_episode_steps) { *reward = (e->flag == 0) ? 0.0 : 100.0; return 1; } /* :144-147 / :227-231 */
     {   /* calculate_number_hanger_area :317-332, relative_state_to_absolute_state :334-343 */

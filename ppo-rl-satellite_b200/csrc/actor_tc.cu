@@ -11,15 +11,19 @@
 //     A B ~= A_lo B_hi + A_hi B_lo + A_hi B_hi            (the dropped A_lo B_lo term is ~2^-22 relative).
 // tests/test_gpu_actor_tc.py measures the error of this path and of the FFMA2 path against an fp64 ground truth.
 //
-// One CTA = 128 observations (= the 128 TMEM lanes), 160 threads:
-//   warps 0-3 (thread t = row t): rebuild / load the observation, layer 1 (18 -> 256, CUDA-core FFMA) in chunks of 32
-//             hidden units, tanh, TF32 hi/lo split, written as the K-major, 128-byte-swizzled A operand of the chunk;
-//             later the epilogue: tcgen05.ld of the row's 256 accumulators, bias, tanh, the 3 head dot products,
-//             Philox Gaussian sample, log-prob (one thread owns one whole row: no cross-thread reduction);
-//   warp 4, one elected lane: streams the pre-split, pre-swizzled W2 image (64 KB per K-chunk: hi | lo) into a two-stage
+// One CTA = 128 observations (= the 128 TMEM lanes), 544 threads:
+//   warps 0-15 (thread = row r = tid & 127, quarter p = tid >> 7): rebuild / load the observation, layer 1 (18 -> 256,
+//             CUDA-core FFMA) in chunks of 32 hidden units (8 per thread), tanh, TF32 hi/lo split, written as the K-major,
+//             128-byte-swizzled A operand of the chunk; later the epilogue: tcgen05.ld of 64 of the row's accumulator
+//             columns (a warp may only touch TMEM lanes 32 (w % 4) .. +31, which is exactly its rows), bias, tanh, partial
+//             head dot products, reduced over the four quarters through shared memory; thread (r, p < 3) then finishes
+//             action p: Philox Gaussian sample, clamp, log-prob;
+//   warp 16, one elected lane: streams the pre-split, pre-swizzled W2 image (64 KB per K-chunk: hi | lo) into a two-stage
 //             shared-memory ring with cp.async.bulk + mbarrier and issues the 12 tcgen05.mma (M 128, N 256, K 8) of each
 //             chunk; tcgen05.commit hands the stage back and finally signals the epilogue.
-// Shared memory: A 2 x 32 KB, B 2 x 64 KB, W1^T 18 KB, W3 / biases 6 KB = 216 KB -> one CTA per SM; TMEM: 256 columns.
+// The large product A_hi B_hi and the two small cross terms go to SEPARATE TMEM accumulators: the tensor core's fp32
+// accumulation truncates, and with all 96 accumulations in one place that bias was the dominant error (measured).
+// Shared memory: A 2 x 32 KB, B 2 x 64 KB, W1^T 18 KB, W3 / biases 6 KB = 216 KB -> one CTA per SM; TMEM: 512 columns.
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "sat_math.cuh"
@@ -31,7 +35,9 @@ using namespace mlp;
 constexpr int TM = 128;                         // rows per CTA
 constexpr int KC = 32;                          // hidden units (K) per chunk = one 128-byte swizzle row of TF32
 constexpr int NCH = HID / KC;                   // 8 chunks
-constexpr int TC_THREADS = 160;
+constexpr int NPART = 4;                        // threads per row
+constexpr int TC_COMPUTE = TM * NPART;          // 512
+constexpr int TC_THREADS = TC_COMPUTE + 32;
 constexpr int A_BYTES = TM * 128;               // one chunk of A, hi or lo
 constexpr int B_BYTES = HID * 128;              // one chunk of B, hi or lo
 constexpr int OFF_A = 0;                        // [stage][hi/lo][A_BYTES]
@@ -44,7 +50,7 @@ constexpr int OFF_BAR = OFF_B2S + HID * 4;      // mbarriers
 constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
 constexpr int TC_SMEM = OFF_TMEM + 16 + 1024;   // + slack for the 1024-byte alignment of the swizzled tiles
 static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemCols = 512;             // [0, 256): A_hi B_hi; [256, 512): A_lo B_hi + A_hi B_lo
 // tcgen05 instruction descriptor (cute/arch/mma_sm100_desc.hpp, InstrDescriptor): D fp32 (bit 4), A and B TF32 (2 << 7, 2 << 10),
 // both K-major (bits 15, 16 = 0), N = 256 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -69,6 +75,16 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the two MUFU units, 5 instructions, abs. error ~1e-7 (inf / 0 saturate to +-1 by themselves)
+__device__ __forceinline__ float tanh5(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+template <bool TANH>
+__device__ __forceinline__ float act_fn(float x) { return TANH ? tanh5(x) : fmaxf(x, 0.0f); }
+
 // 32 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -103,13 +119,16 @@ __global__ void actor_tc_pack_kernel(const float* __restrict__ packed, uint32_t*
     chunk[(B_BYTES + off) >> 2] = lo;
 }
 
+template <bool TANH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 actor_tc_kernel(const float* __restrict__ packed, const uint32_t* __restrict__ image, const float* __restrict__ obs_f32,
                 const SatEnvState st, const double* __restrict__ obs_stats, int64_t n, int64_t row_offset, uint64_t seed,
-                uint64_t step, float max_action, int use_tanh, const float* __restrict__ eps_in, float* __restrict__ act,
+                uint64_t step, float max_action, const float* __restrict__ eps_in, float* __restrict__ act,
                 float* __restrict__ logp, float* __restrict__ mean_out, float* __restrict__ eps_out, float* __restrict__ obs_out) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the swizzled tiles by pointer arithmetic on the shared array (an integer round trip would turn
+    // every access into a generic-space LD/ST: measured 14 % of the kernel's instructions)
+    unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     float* w1s = reinterpret_cast<float*>(sm + OFF_W1);
     float* w3s = reinterpret_cast<float*>(sm + OFF_W3S);
     float* b1s = reinterpret_cast<float*>(sm + OFF_B1S);
@@ -126,12 +145,12 @@ actor_tc_kernel(const float* __restrict__ packed, const uint32_t* __restrict__ i
 
     if (tid == 0) {
         mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1);
-        mbar_init(&a_full[0], TM); mbar_init(&a_full[1], TM);
+        mbar_init(&a_full[0], TC_COMPUTE); mbar_init(&a_full[1], TC_COMPUTE);
         mbar_init(&ab_empty[0], 1); mbar_init(&ab_empty[1], 1);
         mbar_init(d_full, 1); mbar_init(misc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC_COMPUTE / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -141,9 +160,9 @@ actor_tc_kernel(const float* __restrict__ packed, const uint32_t* __restrict__ i
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == TC_COMPUTE / 32) {
         // ------------------------------------------------------------------ control lane: W2 stream + MMA issue
-        if (tid == TM) {
+        if (tid == TC_COMPUTE) {
             mbar_expect_tx(misc, IN * HID * 4 + ACTP * HID * 4);
             bulk_g2s(w1s, packed + OFF_W1T, IN * HID * 4, misc);
             bulk_g2s(w3s, packed + OFF_W3, ACTP * HID * 4, misc);
@@ -161,9 +180,9 @@ actor_tc_kernel(const float* __restrict__ packed, const uint32_t* __restrict__ i
 #pragma unroll
                 for (int kk = 0; kk < KC / 8; ++kk) {                    // UMMA K = 8 TF32 = 32 bytes along the swizzled row
                     const uint32_t o = kk * 32;
-                    umma_tf32(tmem_d, umma_desc(a_lo + o), umma_desc(b_hi + o), (kc | kk) ? 1u : 0u);   // small terms first
-                    umma_tf32(tmem_d, umma_desc(a_hi + o), umma_desc(b_lo + o), 1u);
-                    umma_tf32(tmem_d, umma_desc(a_hi + o), umma_desc(b_hi + o), 1u);
+                    umma_tf32(tmem_d + HID, umma_desc(a_lo + o), umma_desc(b_hi + o), (kc | kk) ? 1u : 0u);   // cross terms
+                    umma_tf32(tmem_d + HID, umma_desc(a_hi + o), umma_desc(b_lo + o), 1u);
+                    umma_tf32(tmem_d, umma_desc(a_hi + o), umma_desc(b_hi + o), (kc | kk) ? 1u : 0u);         // main term
                 }
                 umma_commit(&ab_empty[s]);                               // arrives when these MMAs have read their operands
                 if (kc == NCH - 1) umma_commit(d_full);
@@ -178,7 +197,8 @@ actor_tc_kernel(const float* __restrict__ packed, const uint32_t* __restrict__ i
         }
     } else {
         // ------------------------------------------------------------------ rows: observation, layer 1, A operand
-        int64_t g = row0 + tid;
+        const int r = tid & (TM - 1), part = tid >> 7;
+        int64_t g = row0 + r;
         const bool live = g < n;
         if (!live) g = n - 1;
         float x[IN];
@@ -202,25 +222,27 @@ actor_tc_kernel(const float* __restrict__ packed, const uint32_t* __restrict__ i
                 x[d] = (float)y;
             }
         }
-        if (obs_out && live) {
+        if (obs_out && live && part == 0) {
 #pragma unroll
             for (int d = 0; d < IN; ++d) obs_out[g * IN + d] = x[d];
         }
         mbar_wait(misc, 0);
-        const int r8 = tid & 7;
-        const uint32_t row_off = (uint32_t)(tid >> 3) * 1024u + (uint32_t)r8 * 128u;
+        const int r8 = r & 7;
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)r8 * 128u;
+        constexpr int UPT = KC / NPART;                 // hidden units per thread per chunk: 8 = two 16-byte swizzle chunks
 #pragma unroll 1
         for (int kc = 0; kc < NCH; ++kc) {
             const int s = kc & 1;
-            float h[KC];
+            const int j0 = kc * KC + part * UPT;
+            float h[UPT];
 #pragma unroll
-            for (int j = 0; j < KC; ++j) h[j] = b1s[kc * KC + j];
+            for (int j = 0; j < UPT; ++j) h[j] = b1s[j0 + j];
 #pragma unroll
             for (int k = 0; k < IN; ++k) {
                 const float xv = x[k];
-                const float4* wrow = reinterpret_cast<const float4*>(w1s + k * HID + kc * KC);      // broadcast reads
+                const float4* wrow = reinterpret_cast<const float4*>(w1s + k * HID + j0);
 #pragma unroll
-                for (int q = 0; q < KC / 4; ++q) {
+                for (int q = 0; q < UPT / 4; ++q) {
                     const float4 w = wrow[q];
                     h[4 * q] = fmaf(xv, w.x, h[4 * q]); h[4 * q + 1] = fmaf(xv, w.y, h[4 * q + 1]);
                     h[4 * q + 2] = fmaf(xv, w.z, h[4 * q + 2]); h[4 * q + 3] = fmaf(xv, w.w, h[4 * q + 3]);
@@ -229,13 +251,14 @@ actor_tc_kernel(const float* __restrict__ packed, const uint32_t* __restrict__ i
             if (kc >= 2) mbar_wait(&ab_empty[s], ((kc >> 1) - 1) & 1);   // the MMAs of chunk kc - 2 have consumed this stage
             unsigned char* a_hi = sm + OFF_A + s * 2 * A_BYTES + row_off;
 #pragma unroll
-            for (int c = 0; c < KC / 4; ++c) {
+            for (int q = 0; q < UPT / 4; ++q) {
+                const int c = part * (UPT / 4) + q;                      // 16-byte chunk of the row's 128 bytes
                 uint4 hi, lo;
                 float v;
-                v = activate(h[4 * c], use_tanh);     hi.x = to_tf32(v); lo.x = to_tf32(v - __uint_as_float(hi.x));
-                v = activate(h[4 * c + 1], use_tanh); hi.y = to_tf32(v); lo.y = to_tf32(v - __uint_as_float(hi.y));
-                v = activate(h[4 * c + 2], use_tanh); hi.z = to_tf32(v); lo.z = to_tf32(v - __uint_as_float(hi.z));
-                v = activate(h[4 * c + 3], use_tanh); hi.w = to_tf32(v); lo.w = to_tf32(v - __uint_as_float(hi.w));
+                v = act_fn<TANH>(h[4 * q]);     hi.x = to_tf32(v); lo.x = to_tf32(v - __uint_as_float(hi.x));
+                v = act_fn<TANH>(h[4 * q + 1]); hi.y = to_tf32(v); lo.y = to_tf32(v - __uint_as_float(hi.y));
+                v = act_fn<TANH>(h[4 * q + 2]); hi.z = to_tf32(v); lo.z = to_tf32(v - __uint_as_float(hi.z));
+                v = act_fn<TANH>(h[4 * q + 3]); hi.w = to_tf32(v); lo.w = to_tf32(v - __uint_as_float(hi.w));
                 const uint32_t sw = (uint32_t)((c ^ r8) << 4);
                 *reinterpret_cast<uint4*>(a_hi + sw) = hi;
                 *reinterpret_cast<uint4*>(a_hi + A_BYTES + sw) = lo;
@@ -245,53 +268,67 @@ actor_tc_kernel(const float* __restrict__ packed, const uint32_t* __restrict__ i
         }
 
         // ------------------------------------------------------------------ epilogue: h2 = act(D + b2), heads, sample
+        // head weights and the second bias interleaved per hidden unit, so the epilogue needs one broadcast load per column.
+        // The table reuses the W1^T region: every compute thread is past layer 1 at the barrier (the operand rings cannot be
+        // reused yet - the last chunk's MMAs may still be reading them)
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
+        float4* w3p = reinterpret_cast<float4*>(w1s);
+        if (tid < HID) w3p[tid] = make_float4(w3s[tid], w3s[HID + tid], w3s[2 * HID + tid], b2s[tid]);
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
         mbar_wait(d_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float pre[3] = {0.0f, 0.0f, 0.0f};
-        const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+        constexpr int CPT = HID / NPART;                // accumulator columns per thread: 64
 #pragma unroll 1
-        for (int cb = 0; cb < HID / 32; ++cb) {
-            float v[32];
-            tmem_ld32(lane_base + (uint32_t)(cb * 32), v);
+        for (int cb = 0; cb < CPT / 32; ++cb) {
+            const int c0 = part * CPT + cb * 32;
+            float v[32], u[32];
+            tmem_ld32(lane_base + (uint32_t)c0, v);
+            tmem_ld32(lane_base + (uint32_t)(HID + c0), u);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int col = cb * 32 + j;
-                const float h2 = activate(v[j] + b2s[col], use_tanh);
-                pre[0] = fmaf(h2, w3s[col], pre[0]); pre[1] = fmaf(h2, w3s[HID + col], pre[1]); pre[2] = fmaf(h2, w3s[2 * HID + col], pre[2]);
+                const int col = c0 + j;
+                const float4 wb = w3p[col];                               // (W3[0][col], W3[1][col], W3[2][col], b2[col]): one broadcast load
+                const float h2 = act_fn<TANH>((v[j] + u[j]) + wb.w);
+                pre[0] = fmaf(h2, wb.x, pre[0]); pre[1] = fmaf(h2, wb.y, pre[1]); pre[2] = fmaf(h2, wb.z, pre[2]);
             }
         }
-        if (live) {
-            float eps[4];
-            if (eps_in) { eps[0] = eps_in[g * 3]; eps[1] = eps_in[g * 3 + 1]; eps[2] = eps_in[g * 3 + 2]; }
+        // reduce the four quarters of every row (all MMAs are complete: the A ring is free to be reused as scratch)
+        float* red = reinterpret_cast<float*>(sm + OFF_A);              // [NPART][TM][4]
+        *reinterpret_cast<float4*>(red + (part * TM + r) * 4) = make_float4(pre[0], pre[1], pre[2], 0.0f);
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");   // the 16 compute warps only
+        if (live && part < 3) {
+            const int a = part;
+            const float pre_a = ((red[(0 * TM + r) * 4 + a] + red[(1 * TM + r) * 4 + a]) + red[(2 * TM + r) * 4 + a]) + red[(3 * TM + r) * 4 + a];
+            float eps;
+            if (eps_in) eps = eps_in[g * 3 + a];
             else {
                 const uint64_t gid = (uint64_t)(row_offset + g);
                 uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
                 sat::philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-                const float u0 = ((float)c[0] + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)c[1] + 0.5f) * 2.3283064365386963e-10f;
-                const float u2 = ((float)c[2] + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)c[3] + 0.5f) * 2.3283064365386963e-10f;
-                const float r0 = sqrtf(-2.0f * logf(fminf(u0, 0.99999994f))), r1 = sqrtf(-2.0f * logf(fminf(u2, 0.99999994f)));
-                float s0, c0, s1, c1;
-                sincosf(6.283185307179586f * u1, &s0, &c0);
-                sincosf(6.283185307179586f * u3, &s1, &c1);
-                eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
+                // Box-Muller on (0,1) uniforms: (c0, c1) -> eps 0, 1; (c2, c3) -> eps 2 (same draws as actor.cu)
+                const uint32_t ca = (a == 2) ? c[2] : c[0], cb2 = (a == 2) ? c[3] : c[1];
+                const float ua = ((float)ca + 0.5f) * 2.3283064365386963e-10f, ub = ((float)cb2 + 0.5f) * 2.3283064365386963e-10f;
+                const float rr = sqrtf(-2.0f * logf(fminf(ua, 0.99999994f)));
+                float sn, cs;
+                sincosf(6.283185307179586f * ub, &sn, &cs);
+                eps = rr * ((a == 1) ? sn : cs);
             }
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float mean = max_action * tanhf(pre[a] + __ldg(packed + OFF_B3 + a));                      // :87
-                const float sd = expf(__ldg(packed + OFF_LS + a));                                             // :93
-                float xs = fmaf(sd, eps[a], mean);                                                             // :186
-                xs = fminf(fmaxf(xs, -max_action), max_action);                                                // :187
-                const float diff = xs - mean;
-                const float lp = -(diff * diff) / (2.0f * sd * sd) - logf(sd) - 0.9189385332046727f;           // :188
-                act[g * 3 + a] = xs; logp[g * 3 + a] = lp;
-                if (mean_out) mean_out[g * 3 + a] = mean;
-                if (eps_out) eps_out[g * 3 + a] = eps[a];
-            }
+            const float mean = max_action * tanhf(pre_a + __ldg(packed + OFF_B3 + a));                        // :87
+            const float sd = expf(__ldg(packed + OFF_LS + a));                                               // :93
+            float xs = fmaf(sd, eps, mean);                                                                  // :186
+            xs = fminf(fmaxf(xs, -max_action), max_action);                                                  // :187
+            const float diff = xs - mean;
+            const float lp = -(diff * diff) / (2.0f * sd * sd) - logf(sd) - 0.9189385332046727f;             // :188
+            act[g * 3 + a] = xs; logp[g * 3 + a] = lp;
+            if (mean_out) mean_out[g * 3 + a] = mean;
+            if (eps_out) eps_out[g * 3 + a] = eps;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_COMPUTE / 32) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
     }
 }
@@ -318,7 +355,9 @@ int sat_actor_sample_tc(const SatActorWeights* w, float* tc_image, const float* 
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev < 0 || dev >= 64 || !done[dev]) {
-        e = cudaFuncSetAttribute(actor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        e = cudaFuncSetAttribute(actor_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(actor_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
         if (e != cudaSuccess) return (int)e;
         if (dev >= 0 && dev < 64) done[dev] = 1;
     }
@@ -330,9 +369,14 @@ int sat_actor_sample_tc(const SatActorWeights* w, float* tc_image, const float* 
     SatEnvState s0 = {};
     if (!obs_f32) s0 = *st;
     const unsigned blocks = (unsigned)((n + TM - 1) / TM);
-    actor_tc_kernel<<<blocks, TC_THREADS, TC_SMEM, s>>>(w->packed, reinterpret_cast<const uint32_t*>(tc_image), obs_f32, s0, obs_stats,
-                                                        n, row_offset, seed, step, w->max_action, w->use_tanh, eps_in, act, logp,
-                                                        mean_out, eps_out, obs_out);
+    if (w->use_tanh)
+        actor_tc_kernel<true><<<blocks, TC_THREADS, TC_SMEM, s>>>(w->packed, reinterpret_cast<const uint32_t*>(tc_image), obs_f32, s0,
+                                                                  obs_stats, n, row_offset, seed, step, w->max_action, eps_in, act,
+                                                                  logp, mean_out, eps_out, obs_out);
+    else
+        actor_tc_kernel<false><<<blocks, TC_THREADS, TC_SMEM, s>>>(w->packed, reinterpret_cast<const uint32_t*>(tc_image), obs_f32, s0,
+                                                                   obs_stats, n, row_offset, seed, step, w->max_action, eps_in, act,
+                                                                   logp, mean_out, eps_out, obs_out);
     return launch_status();
 }
 

@@ -80,7 +80,7 @@ SAT_DEV void load_and_gate(const SatEnvState& st, const SatEnvParams& p, const A
         for (int k = 0; k < 3; ++k) L.a[k] = clip16((double)(raw ? raw[k] : act[e * 3 + k]));
     }
     bool frozen;                                            // gating uses LAST step's dis / dangerous_zone (Q3)
-    if (p.flag == 0) frozen = (craft == 0) && (dis_stale < p.d_range) && (dz_stale != 0);   // :91-96
+    if (p.flag != 1) frozen = (craft == 0) && (dis_stale < p.d_range) && (dz_stale != 0);   // :91-96 (Flag 2: :265-277)
     else frozen = (craft == 1) && (dz_stale == 0);                                          // :190-198
     if (frozen) { L.a[0] = 0.0; L.a[1] = 0.0; L.a[2] = 0.0; }
     if (!do_impulse) return;
@@ -359,7 +359,8 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     }
 
     // ---------------- danger-zone count (:150 -> :317-332), three phases with CTA-wide solve compaction
-    const bool need_dz = !done && !p.skip_danger_zone;
+    // Flag 2 (environment.py:257-298, the dynamics in front of the surrogate training): no danger-zone evaluation, reward 0
+    const bool need_dz = !done && !p.skip_danger_zone && p.flag != 2;
     DzNode nd;
     {
         double Ri[3], Vi[3];
@@ -383,7 +384,8 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
 
     // ---------------- reward (:139-147, :161-175, Flag 1 :221-251)
     double reward = 0.0, cos_a = 0.0, cos_b = 0.0;
-    if (captured) reward = (p.flag == 0) ? 100.0 : -150.0;
+    if (p.flag == 2) reward = 0.0;                                                            // :303-316
+    else if (captured) reward = (p.flag == 0) ? 100.0 : -150.0;
     else if (timeout) reward = (p.flag == 0) ? 0.0 : 100.0;
     else {
         // the four cosines are split over the lane pair (2 each) and swapped: same values, half the latency. The operands
@@ -403,7 +405,7 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     }
     // (warp-convergent point: the swaps below are executed by every lane)
     const double oth_a = shfl1(cos_a), oth_b = shfl1(cos_b);
-    if (!captured && !timeout) {
+    if (!captured && !timeout && p.flag != 2) {
         const double pv1 = craft == 0 ? cos_a : oth_a, pv2 = craft == 0 ? cos_b : oth_b;
         const double pv3 = craft == 0 ? oth_a : cos_a, pv4 = craft == 0 ? oth_b : cos_b;
         const double ra = (dis < L.dis_prev) ? 1.0 : -1.0;                                    // :161
@@ -824,7 +826,7 @@ int env_step_impl(const SatEnvState* st, const void* pa, const void* ea, const i
     if ((want_stats || p->mode == SAT_MODE_RK4) && !workspace) return SAT_ERR_NULL;
     if (p->mode != SAT_MODE_CW && p->mode != SAT_MODE_RK4) return SAT_ERR_MODE;
     if (p->action_dtype != SAT_ACT_F32 && p->action_dtype != SAT_ACT_F64) return SAT_ERR_MODE;
-    if (p->flag != 0 && p->flag != 1) return SAT_ERR_MODE;
+    if (p->flag < 0 || p->flag > 2) return SAT_ERR_MODE;
     if (p->mode == SAT_MODE_RK4 && p->substeps < 1) return SAT_ERR_SIZE;
     if (workspace && ((uintptr_t)workspace & 15)) return SAT_ERR_SIZE;
     cudaStream_t s = (cudaStream_t)stream;

@@ -6,7 +6,8 @@ Same constructor, attributes and reset/step contract as the reference (environme
     s_, r, done = env.step(pursuer_action, escaper_action, epsiode_count)
 One environment = a batch of size 1 on the GPU (cw mode: the propagation the shipped env uses). The batched
 engine lives in ppo_rl_satellite_b200.engine.EnvBatch; there is no CPU path.
-Not replicated: the per-step print (environment.py:134) and Flag == 2 (surrogate-network training, out of scope).
+Not replicated: the per-step print (environment.py:134) and, under Flag == 2, the surrogate-network fit (:295-301; the
+step's dynamics themselves are).
 """
 import numpy as np
 
@@ -42,7 +43,7 @@ class satellites:
         self.burn_reward, self.win_reward = 0, 100
         self.max_episode_steps = args.max_episode_steps
         self.ellipse_params = []
-        self._env = _eng.EnvBatch(1, mode="cw", flag=0 if Flag not in (0, 1) else Flag, d_capture=d_capture,
+        self._env = _eng.EnvBatch(1, mode="cw", flag=Flag if Flag in (0, 1, 2) else 0, d_capture=d_capture,
                                   d_range=d_range, fuel_c=fuel_c, fuel_t=fuel_t,
                                   max_episode_steps=self.max_episode_steps, auto_reset=False)
         self._cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -73,8 +74,10 @@ class satellites:
     dangerous_zone = property(lambda self: int(self._env.dangerous_zone[0]))
 
     def reset(self, Flag):
-        if Flag not in (0, 1):
-            raise NotImplementedError("Flag == 2 (reachable-domain surrogate training) is outside the CUDA hot path")
+        if Flag not in (0, 1, 2):
+            raise ValueError("Flag must be 0, 1 or 2")
+        # Flag 2 (environment.py:257-316): the step's dynamics (gating, impulse, fuel, CW propagation, terminal checks, reward 0)
+        # run on the device; the reachable-domain surrogate fit the reference interleaves (:295-301) is outside the hot path
         self.Flag = Flag
         self._env.reset(flag=Flag)
         self.pursuer_reward = 0.0
@@ -91,6 +94,8 @@ class satellites:
         reward, done = float(out[18]), bool(out[19])
         if self.Flag == 0:
             self.pursuer_reward = reward
+        elif self.Flag == 2:
+            self.pursuer_reward = 0
         else:
             self.escaper_reward, self.pursuer_reward = reward, -reward
         return out[:18].copy(), reward, done

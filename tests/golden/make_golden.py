@@ -164,6 +164,42 @@ def gen_env():
     save("env_golden.npz", **out)
 
 
+def gen_env_flag2():
+    """Flag 2 (environment.py:257-316): the reference's own step with the two surrogate calls (:299 numerical_method_process,
+    :301 trian_elliptical_fitting.train - the reachable-domain network fit, outside the hot path) replaced by no-ops.
+    Phase A = 80 Flag-0 steps from reset(0), so that fuel / dis / dangerous_zone (which persist through reset, Q2, and gate the
+    Flag-2 impulse) are non-trivial; phase B = reset(2) and 500 Flag-2 steps with resets on done."""
+    mods = refshim.load()
+    mods["environment"].real_time_data_process.numerical_method_process = lambda *a, **k: None
+    env = refshim.make_env(d_capture=181200, max_episode_steps=60)
+    env.trian_elliptical_fitting.train = lambda *a, **k: None
+    env.d_range = 250000.0          # > the 182 km starting distance: the "pursuer frozen" gating branch (:265-270) is exercised
+    rng = np.random.default_rng(29)
+    nA, nB = 80, 500
+    n = nA + nB
+    pa = rng.uniform(-2, 2, (n, 3)).astype(np.float32).astype(np.float64)
+    ea = rng.uniform(-2, 2, (n, 3)).astype(np.float32).astype(np.float64)
+    flags = np.array([0] * nA + [2] * nB, dtype=np.int32)
+    obs, rew, done, dz, fuel_c, fuel_t, dis, cnts = [], [], [], [], [], [], [], []
+    env.reset(0)
+    cnt = 0
+    for t in range(n):
+        if t == nA:
+            env.reset(2); cnt = 0
+        cnt += 1
+        s_, r, d = refshim.quiet_step(env, pa[t], ea[t], cnt)
+        obs.append(np.asarray(s_, dtype=np.float64)); rew.append(float(r)); done.append(bool(d))
+        dz.append(int(env.dangerous_zone)); fuel_c.append(float(env.fuel_c)); fuel_t.append(float(env.fuel_t))
+        dis.append(float(env.dis)); cnts.append(cnt)
+        if d:
+            env.reset(int(flags[t])); cnt = 0
+    save("env_flag2_golden.npz", pa=pa, ea=ea, flag=flags, obs=np.array(obs), reward=np.array(rew), done=np.array(done),
+         dz=np.array(dz, dtype=np.int32), fuel_c=np.array(fuel_c), fuel_t=np.array(fuel_t), dis=np.array(dis),
+         count=np.array(cnts, dtype=np.int32), d_capture=np.float64(181200), d_range=np.float64(250000),
+         max_episode_steps=np.int32(60))
+    print("flag2: episodes", int(np.sum(done[nA:])), "frozen-pursuer steps", int(np.sum((np.array(dz[nA - 1:-1]) != 0))), "dz hist", np.bincount(dz, minlength=3))
+
+
 # --------------------------------------------------------------------------------------------
 def gen_fsolve_dz():
     sf = refshim.load()["satellite_function"]
@@ -338,10 +374,11 @@ def gen_reach():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rk4", "elements", "env", "danger", "ppo", "norm", "ode", "reach"]
+    which = sys.argv[1:] or ["rk4", "elements", "env", "flag2", "danger", "ppo", "norm", "ode", "reach"]
     if "rk4" in which: gen_rk4()
     if "elements" in which: gen_elements()
     if "env" in which: gen_env()
+    if "flag2" in which: gen_env_flag2()
     if "danger" in which: gen_fsolve_dz()
     if "ppo" in which: gen_ppo()
     if "norm" in which: gen_norm()

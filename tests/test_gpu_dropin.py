@@ -60,8 +60,26 @@ def test_satellites_reset_step_contract_matches_reference_rollout(golden, mods):
         if d:
             env.reset(0)
             cnt = 0
-    with pytest.raises(NotImplementedError):
-        env.reset(2)
+    with pytest.raises(ValueError):
+        env.reset(3)
+
+
+def test_satellites_flag2_dynamics_match_reference(golden, mods):
+    """reset(2) / step under Flag 2 (environment.py:257-316): gating by the stale dis / dangerous_zone, impulse, fuel, CW
+    propagation, terminal checks, reward 0 - the recorded reference stream (surrogate fit stubbed), bit for bit."""
+    g = golden("env_flag2_golden.npz")
+    env = mods.environment.satellites(d_capture=50000, args=Args(max_episode_steps=int(g["max_episode_steps"])))
+    env.d_capture = float(g["d_capture"])
+    env.d_range = float(g["d_range"])
+    env.reset(0)
+    for t in range(len(g["flag"])):
+        if t > 0 and g["flag"][t] != g["flag"][t - 1]:
+            env.reset(int(g["flag"][t]))
+        s_, r, d = env.step(g["pa"][t], g["ea"][t], int(g["count"][t]))
+        assert np.array_equal(s_, g["obs"][t]) and r == g["reward"][t] and d == bool(g["done"][t]), t
+        assert env.dangerous_zone == g["dz"][t] and env.fuel_c == g["fuel_c"][t] and env.fuel_t == g["fuel_t"][t] and env.dis == g["dis"][t], t
+        if d:
+            env.reset(int(g["flag"][t]))
 
 
 def test_driver_loop_like_cppo_main(golden, mods, tmp_path):

@@ -188,3 +188,22 @@ def test_reachable_domain_sweep_matches_reference(golden, oracle):
         assert hi.shape == g[f"rf_max_{n}"].shape and valid.sum() > 10
         np.testing.assert_allclose(hi, g[f"rf_max_{n}"], rtol=1e-12, atol=1e-6)
         np.testing.assert_allclose(lo, g[f"rf_min_{n}"], rtol=1e-12, atol=1e-6)
+
+
+def test_env_flag2_dynamics_match_reference(golden, oracle):
+    """Flag 2 (environment.py:257-316; the two surrogate-fit calls stubbed when the fixture was recorded): 80 Flag-0 steps,
+    then reset(2) and 500 Flag-2 steps, bit for bit (obs, reward, done, persistent dz / fuel / dis)."""
+    g = golden("env_flag2_golden.npz")
+    eg = golden("env_golden.npz")
+    env = oracle.Env(d_capture=float(g["d_capture"]), d_range=float(g["d_range"]), max_episode_steps=int(g["max_episode_steps"]),
+                     M=eg["stm100_columns"])
+    env.reset(0)
+    for t in range(len(g["flag"])):
+        if t > 0 and g["flag"][t] != g["flag"][t - 1]:
+            env.reset(int(g["flag"][t]))
+        o, r, d = env.step(g["pa"][t], g["ea"][t], int(g["count"][t]))
+        assert np.array_equal(o, g["obs"][t]) and r == g["reward"][t] and d == bool(g["done"][t]), t
+        assert env.e.dangerous_zone == g["dz"][t] and env.e.fuel_c == g["fuel_c"][t] and env.e.dis == g["dis"][t], t
+        if d:
+            env.reset(int(g["flag"][t]))
+    assert (g["flag"] == 2).sum() == 500 and g["done"][80:].sum() >= 5
