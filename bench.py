@@ -458,12 +458,12 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     row_offset = rank * n
 
-    def full_step(t):
+    def full_step(t, tc=False):
         k = t % RING
         pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=t, row_offset=row_offset,
-                       act=buf_act[k], logp=buf_logp[k], obs_out=buf_obs[k])
+                       act=buf_act[k], logp=buf_logp[k], obs_out=buf_obs[k], tc=tc)
         evader.sample(env=env, obs_stats=obs_stats, seed=12, step=t, row_offset=row_offset,
-                      act=buf_eact[k], logp=buf_elogp[k])
+                      act=buf_eact[k], logp=buf_elogp[k], tc=tc)
         env.step(buf_act[k], buf_eact[k], reward=buf_rew[k], done=buf_done[k], obs_stats=obs_stats,
                  ret_stats=ret_stats, ret_std_out=buf_rstd[k:k + 1])
 
@@ -535,6 +535,11 @@ def run_ours(args, rank, world, local_rank):
         full_step(cnt[0]); cnt[0] += 1
     t_full, t_full_min = time_kernel(_full)
     t_act, t_act_min = time_kernel(lambda: pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=0, act=buf_act[k], logp=buf_logp[k]))
+    # opt-in variant: the actors' hidden layer as 3xTF32 on the tensor cores (csrc/actor_tc.cu)
+    def _full_tc():
+        full_step(cnt[0], tc=True); cnt[0] += 1
+    t_full_tc, t_full_tc_min = time_kernel(_full_tc)
+    t_act_tc, _ = time_kernel(lambda: pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=0, act=buf_act[k], logp=buf_logp[k], tc=True))
     # the same full step as 4 independent env shards ("virtual ranks": own running statistics, own stream) so that the
     # FP32 actor kernels of one shard overlap the FP64 env kernels of another
     def sharded_full_step_ms(parts_n=4, K=10):
@@ -708,6 +713,13 @@ def run_ours(args, rank, world, local_rank):
                          "peak_source": "nominal FP32 pipe rate 148 SMs x 128 FFMA lanes x 2 x 1.965 GHz",
                          "measured_ffma_chain_tflops": peak32, "frac_of_measured_chain": ach_act / peak32, "launch_ms": t_act,
                          "traffic": traffic_actor, "traffic_source": traffic_actor_src},
+            "tensor_core_actor_variant": {
+                "what": "the same full step with both actors' 256 x 256 hidden layer on tcgen05 tensor cores (3xTF32, accumulators in TMEM; "
+                        "opt-in: GaussianActorKernel.sample(tc=True) / SAT_ACTOR_TC=1). Not the default: its error against an fp64 ground "
+                        "truth is 1.6x (tanh) / 2.0x (ReLU) the FFMA2 path's rms (tests/test_gpu_actor_tc.py); same Philox stream",
+                "ms_per_step": t_full_tc, "ms_per_step_min": t_full_tc_min, "per_gpu_env_steps_per_sec": n / (t_full_tc * 1e-3),
+                "actor_launch_ms": t_act_tc, "actor_speedup_vs_ffma2": t_act / t_act_tc,
+                "actor_useful_tflops": ach_act * t_act / t_act_tc},
             "as_4_independent_shards_on_4_streams": None if t_full4 is None else {
                 "ms_per_step": t_full4, "per_gpu_env_steps_per_sec": n / (t_full4 * 1e-3),
                 "what": "the same work as 4 env shards with per-shard running statistics on 4 streams: the FP32 actor kernels of "
