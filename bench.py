@@ -520,6 +520,13 @@ def run_ours(args, rank, world, local_rank):
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts)), float(np.min(ts))
 
+    # opt-in fast-libm variant of the same step (SatEnvParams.fast_libm: libdevice instead of the host libm's arithmetic in the
+    # danger-zone count; not bit-identical to the reference there) on an identical second batch
+    env_fast = eng.EnvBatch(n, mode="rk4", substeps=S, h=1.0, d_capture=20000.0, max_episode_steps=1000, auto_reset=True, device=dev,
+                            fast_libm=True)
+    env_fast.set_state(P, rng.normal(0, 3.0, (n, 3)), E, rng.normal(0, 3.0, (n, 3)))
+    t_env_fast, _ = time_kernel(lambda: env_fast.step(rnd_pa[0], rnd_ea[0], obs_f32=buf_obs[0], reward=buf_rew[0], done=buf_done[0]))
+    del env_fast
     k = 0
     t_env, t_env_min = time_kernel(lambda: env.step(rnd_pa[k], rnd_ea[k], obs_f32=buf_obs[k], reward=buf_rew[k], done=buf_done[k]))
     # per-launch split of the env step, CUDA events recorded between the launches on the launching stream
@@ -735,7 +742,11 @@ def run_ours(args, rank, world, local_rank):
             "actor_kernel (K3, one actor)": {"ms": t_act, "bound": "fp32", "achieved_tflops": ach_act,
                                              "frac_of_nominal_fp32_peak": ach_act / FP32_NOMINAL_TFLOPS,
                                              "frac_of_measured_ffma_chain": ach_act / peak32},
-            "env_step_kernel<rk4> (K2)": {"ms": t_env, "env_steps_per_sec": n / (t_env * 1e-3)},
+            "env_step_kernel<rk4> (K2)": {"ms": t_env, "env_steps_per_sec": n / (t_env * 1e-3),
+                                          "fast_libm_variant": {"ms": t_env_fast, "env_steps_per_sec": n / (t_env_fast * 1e-3),
+                                                                "what": "SatEnvParams.fast_libm = 1 (opt-in): libdevice sin/cos/acos/atan and x*x in the "
+                                                                        "danger-zone count instead of the host libm's own arithmetic; ~3e-5 of the integer "
+                                                                        "counts then differ from the reference (round-1 behaviour). Default = exact"}},
             "gae + advantage normalisation (K4, bound hbm, 17 / 4 / 8 B per sample)": gae_cases,
             "sat_norm_update (65536 x 18 fp64 -> running stats + fp32 normalised)": {
                 "ms": t_norm, "gbs": 65536 * 18 * (8 + 8 + 4) / (t_norm * 1e-3) / 1e9,

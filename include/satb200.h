@@ -76,7 +76,9 @@ typedef struct {
     int32_t action_dtype;       /* SAT_ACT_F32 / SAT_ACT_F64; layout [n][3] */
     int32_t substeps;           /* rk4 mode: RK4 substeps per env step */
     int32_t skip_danger_zone;   /* 1: do not evaluate the danger-zone count (keeps it at its stale value) */
-    int32_t reserved;
+    int32_t fast_libm;          /* 0 (default): the danger-zone path performs the host libm's own arithmetic (csrc/glibm.cuh),
+                                 * the integer count is the reference's bit for bit; 1: CUDA libdevice + x*x (1-2 ulp from the
+                                 * host libm: ~3e-5 of the counts differ), 24 us faster per 65 536-env step */
     double  d_capture, d_range; /* environment.py:35,45 */
     double  gamma;              /* reward-scaling discount (normalization.py:57) */
     double  stm[36];            /* cw mode: row-major 6x6 STM for one step (satellite_function.py:766-773) */

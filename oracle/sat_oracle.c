@@ -21,6 +21,9 @@
  * not correctly rounded: 90 of 1e5 random squares differ by one ulp). Keep the call: the Makefile passes
  * -fno-builtin-pow so that GCC does not fold it into x*x. */
 #define SQ(x) pow((x), 2.0)
+/* The RK4 script is evaluated on numpy ARRAYS in the batched configurations ((6, N) states): there `x ** 2` takes numpy's
+ * fast path np.square = x*x (only exponents 2, 0.5, 1, 0, -1 have one; r ** 3 and r ** 5 stay libm pow). */
+#define SQA(x) ((x) * (x))
 
 /* ------------------------------------------------------------------------------------------
  * numpy / OpenBLAS summation orders (probed in the build container, numpy 2.3.5 +
@@ -49,14 +52,14 @@ static void cross3(const double a[3], const double b[3], double c[3]) {
  * ------------------------------------------------------------------------------------------ */
 void orc_state_eq(const double RV[6], double mu, double Re, double J2, double f[6]) {
     double x = RV[0], y = RV[1], z = RV[2];
-    double r = sqrt(SQ(x) + SQ(y) + SQ(z));                 /* :22 */
+    double r = sqrt(SQA(x) + SQA(y) + SQA(z));              /* :22 */
     double r3 = pow(r, 3.0), r5 = pow(r, 5.0);
     double gx = -mu * x / r3;                               /* :23-25 */
     double gy = -mu * y / r3;
     double gz = -mu * z / r3;
     double zr = z / r;
-    double zr2 = SQ(zr);
-    double c = -3.0 / 2.0 * J2 * SQ(Re) * mu;               /* python evaluates this scalar prefix left to right */
+    double zr2 = SQA(zr);
+    double c = -3.0 / 2.0 * J2 * SQA(Re) * mu;              /* python evaluates this scalar prefix left to right */
     double dgx = c * x / r5 * (1.0 - 5.0 * zr2);            /* :26-28 */
     double dgy = c * y / r5 * (1.0 - 5.0 * zr2);
     double dgz = c * z / r5 * (3.0 - 5.0 * zr2);

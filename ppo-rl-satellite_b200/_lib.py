@@ -29,7 +29,7 @@ class SatEnvState(C.Structure):
 class SatEnvParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("flag", C.c_int32), ("max_episode_steps", C.c_int32),
                 ("auto_reset", C.c_int32), ("action_dtype", C.c_int32), ("substeps", C.c_int32),
-                ("skip_danger_zone", C.c_int32), ("reserved", C.c_int32),
+                ("skip_danger_zone", C.c_int32), ("fast_libm", C.c_int32),
                 ("d_capture", C.c_double), ("d_range", C.c_double), ("gamma", C.c_double),
                 ("stm", C.c_double * 36),
                 ("h", C.c_double), ("mu", C.c_double), ("re", C.c_double), ("j2", C.c_double),

@@ -209,13 +209,14 @@ struct SolveQueue {
     int count, next;
 };
 
+template <bool EXACT = true>
 SAT_DEV void queue_init(SolveQueue& q) {
     if (threadIdx.x == 0) { q.count = 0; q.next = 0; }
     if (threadIdx.x < 4) {
         const int j = threadIdx.x >> 1, k = threadIdx.x & 1;
         const double x0 = dz_guess(j);
         const double h = 1.4901161193847656e-08 * fabs(x0);           // Hybrd1::start_outer
-        const double2 sc = glibm::call::sincos(k ? x0 + h : x0);
+        const double2 sc = Lm<EXACT>::sincos(k ? x0 + h : x0);
         q.trig[j][2 * k] = sc.x; q.trig[j][2 * k + 1] = sc.y;
     }
     __syncthreads();
@@ -241,10 +242,11 @@ SAT_DEV void queue_push(SolveQueue& q, const DzNode& nd, int& slot0, int& slot1,
 #ifndef SAT_SOLVE_WARPS
 #define SAT_SOLVE_WARPS 4
 #endif
+template <bool EXACT = true>
 SAT_DEV void queue_run(SolveQueue& q) {
     const int total = q.count;
     int task = -1;
-    Hybrd1<PFai> hs;
+    Hybrd1<PFaiT<EXACT>> hs;
     // root problems take 5..15 evaluations (mean 8), so a warp runs as long as its slowest lane (12.8 trips measured).
     // Restricting the solve to fewer warps evens the lanes out but lengthens the CTA's serial chain; the kernel is
     // latency-bound, so all four warps is fastest (env step 174 / 176 / 181 / 209 us with 4 / 3 / 2 / 1 solver warps).
@@ -254,7 +256,7 @@ SAT_DEV void queue_run(SolveQueue& q) {
             const int t = atomicAdd(&q.next, 1);
             if (t < total) {
                 task = t;
-                PFai f; f.A = q.A[t]; f.sth = q.sth[t]; f.dvm = q.dvm[t];
+                PFaiT<EXACT> f; f.A = q.A[t]; f.sth = q.sth[t]; f.dvm = q.dvm[t];
                 hs.init_warm(f, dz_guess(q.guess[t]), q.trig[q.guess[t]]);
             } else task = total;                     // queue drained for this lane
         }
@@ -270,7 +272,7 @@ SAT_DEV void queue_run(SolveQueue& q) {
 // partials, auto-reset. environment.py:130-179 / :212-255, :317-343, :346-396.
 // FUSED = true: front half in the same kernel (cw mode, where propagation is one 6x6 product).
 // ---------------------------------------------------------------------------------------------
-template <bool FUSED, typename ActT, int MINB>
+template <bool FUSED, typename ActT, int MINB, bool EXACT>
 __global__ void __launch_bounds__(kBlock, MINB)
 env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* __restrict__ ea,
                 const int32_t* __restrict__ count_override, float* __restrict__ obs_f32,
@@ -284,7 +286,7 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
     __shared__ double tile[kEnvsPerBlock][kStatDims];               // next observation (+ return) of the CTA's envs
     SolveQueue& queue = shm.queue;
     double (&tile_term)[kEnvsPerBlock][kObs] = shm.tile_term;       // pre-reset observation
-    queue_init(queue);
+    queue_init<EXACT>(queue);
 
     const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const int64_t env_raw = tid >> 1;
@@ -366,16 +368,16 @@ env_step_kernel(const SatEnvState st, const ActT* __restrict__ pa, const ActT* _
         double Ri[3], Vi[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { Ri[k] = __dadd_rn(p.r_cw[k], L.r[k]); Vi[k] = __dadd_rn(p.v_cw[k], L.v[k]); }   // :338-341
-        dz_prepare(craft, need_dz, Ri, Vi, fuel_c, p.u_grav, nd);
+        dz_prepare<EXACT>(craft, need_dz, Ri, Vi, fuel_c, p.u_grav, nd);
     }
     int slot0, slot1;
     double alpha0, alpha1;
     queue_push(queue, nd, slot0, slot1, alpha0, alpha1);
-    queue_run(queue);
+    queue_run<EXACT>(queue);
     if (slot0 >= 0) alpha0 = queue.alpha[slot0];
     if (slot1 >= 0) alpha1 = queue.alpha[slot1];
     __syncthreads();                                        // queue storage is reused by the observation tiles below
-    const int dz_eval = dz_finalize(need_dz, nd, alpha0, alpha1, nullptr);
+    const int dz_eval = dz_finalize<EXACT>(need_dz, nd, alpha0, alpha1, nullptr);
     int dz_new = dz_stale;                                   // not refreshed on capture / time-out steps (Q3)
     if (need_dz) {
         if (dz_eval >= 0) dz_new = dz_eval;
@@ -837,14 +839,20 @@ int env_step_impl(const SatEnvState* st, const void* pa, const void* ea, const i
     double* dis_prev = ws ? (double*)(ws + ws_disprev_offset()) : nullptr;
     double* partials = want_stats ? (double*)(ws + ws_partials_offset(n)) : nullptr;
     if (ev) cudaEventRecord(ev[0], s);
+    // exact host-libm arithmetic in the danger-zone path (default) or libdevice (SatEnvParams.fast_libm)
+#define SAT_LAUNCH_FINISH(FUSED, T, ...)                                                                                   \
+    do {                                                                                                                   \
+        if (p->fast_libm) env_step_kernel<FUSED, T, kFinishMinBlocks, false><<<(unsigned)nblocks, kBlock, 0, s>>>(__VA_ARGS__); \
+        else env_step_kernel<FUSED, T, kFinishMinBlocks, true><<<(unsigned)nblocks, kBlock, 0, s>>>(__VA_ARGS__);          \
+    } while (0)
     if (p->mode == SAT_MODE_CW) {
         // one fused kernel: the propagation is a 6x6 product
         if (ev) cudaEventRecord(ev[1], s);
         if (p->action_dtype == SAT_ACT_F32)
-            env_step_kernel<true, float, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
+            SAT_LAUNCH_FINISH(true, float, *st, (const float*)pa, (const float*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, nullptr, partials, ticket, *p);
         else
-            env_step_kernel<true, double, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
+            SAT_LAUNCH_FINISH(true, double, *st, (const double*)pa, (const double*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, nullptr, partials, ticket, *p);
     } else {
         // kernel A (FP64-pipe bound, <= 72 registers, whole batch resident) then kernel B (register-heavy, divergent)
@@ -854,20 +862,21 @@ int env_step_impl(const SatEnvState* st, const void* pa, const void* ea, const i
             env_front_rk4_kernel<float, true><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
                                                                                        dis_prev, obs_early, pa_copy, ea_copy, *p);
             if (front_done) cudaEventRecord(front_done, s);
-            env_step_kernel<false, float, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, pa_copy, ea_copy,
+            SAT_LAUNCH_FINISH(false, float, *st, pa_copy, ea_copy,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
         } else if (p->action_dtype == SAT_ACT_F32) {
             env_front_rk4_kernel<float, false><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea, dis_prev, nullptr, nullptr, nullptr, *p);
             if (ev) cudaEventRecord(ev[1], s);
-            env_step_kernel<false, float, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const float*)pa, (const float*)ea,
+            SAT_LAUNCH_FINISH(false, float, *st, (const float*)pa, (const float*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
         } else {
             env_front_rk4_kernel<double, false><<<(unsigned)fblocks, kFrontBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea, dis_prev, nullptr, nullptr, nullptr, *p);
             if (ev) cudaEventRecord(ev[1], s);
-            env_step_kernel<false, double, kFinishMinBlocks><<<(unsigned)nblocks, kBlock, 0, s>>>(*st, (const double*)pa, (const double*)ea,
+            SAT_LAUNCH_FINISH(false, double, *st, (const double*)pa, (const double*)ea,
                 count_override, obs_f32, obs_f64, term_obs_f64, reward, done, dis_prev, partials, ticket, *p);
         }
     }
+#undef SAT_LAUNCH_FINISH
     rc = launch_status();
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[2], s);

@@ -141,15 +141,38 @@ SAT_DEV void rk4_step(double (&x)[3], double (&v)[3], const Rk4Consts& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// The transcendental calls of the danger-zone path. EXACT = true (default): the host libm's own arithmetic (glibm.cuh) ->
+// the reference's integer count, bit for bit. EXACT = false (SatEnvParams.fast_libm = 1): CUDA's libdevice and x*x, 1-2 ulp
+// from the host libm: ~3e-5 of the counts differ from the reference (round-1 behaviour), 24 us faster per 65 536-env step.
+// ------------------------------------------------------------------------------------------
+template <bool EXACT>
+struct Lm {
+    static SAT_DEV double2 sincos(double x) {
+        if (EXACT) return glibm::call::sincos(x);
+        double s, c; ::sincos(x, &s, &c); return make_double2(s, c);
+    }
+    static SAT_DEV double2 sincos_inline(double x) {          // the solver's single evaluation site
+        double s, c;
+        if (EXACT) glibm::sincos(x, &s, &c); else ::sincos(x, &s, &c);
+        return make_double2(s, c);
+    }
+    static SAT_DEV double cos(double x) { return EXACT ? glibm::call::cos(x) : ::cos(x); }
+    static SAT_DEV double acos(double x) { return EXACT ? glibm::call::acos(x) : ::acos(x); }
+    static SAT_DEV double atan(double x) { return EXACT ? glibm::call::atan(x) : ::atan(x); }
+    static SAT_DEV double pow2(double x) { return EXACT ? glibm::call::pow2(x) : x * x; }
+};
+
+// ------------------------------------------------------------------------------------------
 // orbital elements, satellite_function.py:161-255 (six-element branch; returns false for the
 // circular / parabolic branches, for which the reference's danger-zone code raises)
 // ------------------------------------------------------------------------------------------
 struct Elements { double a, e, i, omega, Omega, f; };
 
+template <bool EXACT = true>
 SAT_DEV bool orbital_elements(double miu, const double R0[3], const double V0[3], Elements& el) {
     double r_norm = norm3(R0), v_norm = norm3(V0);                       // :183-184
     double r_dot_v = dot3(R0, V0);                                       // :185
-    double v2 = glibm::call::pow2(v_norm);                                     // v_norm ** 2 (:186, :193)
+    double v2 = Lm<EXACT>::pow2(v_norm);                                     // v_norm ** 2 (:186, :193)
     double energy = 2.0 / r_norm - v2 / miu;                             // :186
     double c1 = v2 / miu - 1.0 / r_norm, c2 = r_dot_v / miu;             // :193
     double E[3], H[3], N[3];
@@ -163,14 +186,14 @@ SAT_DEV bool orbital_elements(double miu, const double R0[3], const double V0[3]
     if (energy == 0.0 || e == 0.0) return false;
     el.a = 1.0 / fabs(energy);                                           // :188
     el.e = e;
-    el.i = glibm::call::acos(H[2] / h);                                               // :210
-    double omega = (n != 0.0) ? glibm::call::acos(dot3(N, E) / n / e) : 0.0;          // :214-217
+    el.i = Lm<EXACT>::acos(H[2] / h);                                               // :210
+    double omega = (n != 0.0) ? Lm<EXACT>::acos(dot3(N, E) / n / e) : 0.0;          // :214-217
     if (E[2] < 0.0) omega = kTwoPi - omega;                              // :221
     el.omega = omega;
-    double Omega = (n != 0.0) ? glibm::call::acos(N[0] / n) : 0.0;                    // :230-233
+    double Omega = (n != 0.0) ? Lm<EXACT>::acos(N[0] / n) : 0.0;                    // :230-233
     if (N[1] < 0.0) Omega = kTwoPi - Omega;                              // :237
     el.Omega = Omega;
-    double f = glibm::call::acos(dot3(E, R0) / e / r_norm);                           // :242
+    double f = Lm<EXACT>::acos(dot3(E, R0) / e / r_norm);                           // :242
     if (r_dot_v < 0.0) f = kTwoPi - f;
     el.f = f;
     return true;
@@ -181,15 +204,17 @@ SAT_DEV bool orbital_elements(double miu, const double R0[3], const double V0[3]
 // (SURVEY.md Appendix B). f(alpha) = A (dvm cos alpha) + sth (-dvm sin alpha), satellite_function.py:559-562.
 // Returns the iterate un-polished, exactly like the reference uses result[0].
 // ------------------------------------------------------------------------------------------
-struct PFai {
+template <bool EXACT>
+struct PFaiT {
     double A, sth, dvm;
     SAT_DEV double at(double s, double c) const { return A * (dvm * c) + sth * (-dvm * s); }   // given sin, cos of alpha
     SAT_DEV double operator()(double alpha) const {
-        double s, c;
-        glibm::sincos(alpha, &s, &c);
-        return at(s, c);
+        const double2 sc = Lm<EXACT>::sincos_inline(alpha);
+        return at(sc.x, sc.y);
     }
 };
+
+using PFai = PFaiT<true>;
 
 // The iteration is written as a state machine with ONE function-evaluation site per step(): lanes of a
 // warp that are in different phases (initial value / forward-difference Jacobian / trial point) or even on
@@ -349,6 +374,7 @@ struct DzNode {
     double theta, f_cx;     // diagnostics
 };
 
+template <bool EXACT = true>
 SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double Vi[3], double fuel_c,
                         double u_grav, DzNode& nd) {
     nd.status = 0; nd.dvm = 0.0; nd.theta = 0.0; nd.f_cx = 0.0; nd.r_ft = 0.0;
@@ -356,7 +382,7 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     if (!__any_sync(0xffffffffu, active)) return;          // warp-uniform: nothing to evaluate (all done / skipped)
     Elements el_own = {0, 0, 0, 0, 0, 0};
     int ok = 0;
-    if (active) ok = orbital_elements(u_grav, Ri, Vi, el_own) ? 1 : 0;
+    if (active) ok = orbital_elements<EXACT>(u_grav, Ri, Vi, el_own) ? 1 : 0;
     Elements el_oth;
     el_oth.a = __shfl_xor_sync(0xffffffffu, el_own.a, 1); el_oth.e = __shfl_xor_sync(0xffffffffu, el_own.e, 1);
     el_oth.i = __shfl_xor_sync(0xffffffffu, el_own.i, 1); el_oth.omega = __shfl_xor_sync(0xffffffffu, el_own.omega, 1);
@@ -369,12 +395,12 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     // through the same call and swap the results (every lane of the warp takes part in the shuffles; values of
     // inactive lanes are never used).
     // (1) sin/cos of the two inclinations: each lane its own craft's
-    const double2 sci = glibm::call::sincos(el_own.i);
+    const double2 sci = Lm<EXACT>::sincos(el_own.i);
     const double si_x = __shfl_xor_sync(0xffffffffu, sci.x, 1), ci_x = __shfl_xor_sync(0xffffffffu, sci.y, 1);
     const double si_c = lane0 ? sci.x : si_x, ci_c = lane0 ? sci.y : ci_x;
     const double si_t = lane0 ? si_x : sci.x, ci_t = lane0 ? ci_x : sci.y;
     // (2) lane 0: sin/cos of the pursuer's true anomaly; lane 1: of Omega_c - Omega_t
-    const double2 sc2 = glibm::call::sincos(lane0 ? c.f : c.Omega - t.Omega);
+    const double2 sc2 = Lm<EXACT>::sincos(lane0 ? c.f : c.Omega - t.Omega);
     const double s2_x = __shfl_xor_sync(0xffffffffu, sc2.x, 1), c2_x = __shfl_xor_sync(0xffffffffu, sc2.y, 1);
     const double sf0 = lane0 ? sc2.x : s2_x, cf0 = lane0 ? sc2.y : c2_x;
     const double sdo = lane0 ? s2_x : sc2.x, cdo = lane0 ? c2_x : sc2.y;
@@ -385,16 +411,16 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     double temp = (si_a * (lane0 ? sdo : -sdo)) / (ci_a * si_b - si_a * ci_b * cdo);
     const double temp_x = __shfl_xor_sync(0xffffffffu, temp, 1);
     if (isnan(temp) || isnan(temp_x)) temp = 1.0;                        // :331-332 (both are replaced)
-    const double u_own = glibm::call::atan(temp);
+    const double u_own = Lm<EXACT>::atan(temp);
     const double u_x = __shfl_xor_sync(0xffffffffu, u_own, 1);
     const double u_c1 = lane0 ? u_own : u_x, u_t1 = lane0 ? u_x : u_own;
     // (4) squares (python `**`, i.e. libm pow): lane 0 -> e_c^2 and k^2, lane 1 -> e_t^2 and Delta_V_c^2
-    const double e2_own = glibm::call::pow2(el_own.e);
+    const double e2_own = Lm<EXACT>::pow2(el_own.e);
     const double e2_x = __shfl_xor_sync(0xffffffffu, e2_own, 1);
     const double e2_c = lane0 ? e2_own : e2_x, e2_t = lane0 ? e2_x : e2_own;
     const double k = 1.0 + c.e * cf0;
     const double dv = fuel_c;                                             // Delta_V_c (:328)
-    const double sq_own = glibm::call::pow2(lane0 ? k : dv);
+    const double sq_own = Lm<EXACT>::pow2(lane0 ? k : dv);
     const double sq_x = __shfl_xor_sync(0xffffffffu, sq_own, 1);
     const double k2 = lane0 ? sq_own : sq_x, dv2 = lane0 ? sq_x : sq_own;
     // ---- no shuffles below this line
@@ -404,15 +430,15 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
     const double f_cx = (lane0 ? u_c1 : kPi + u_c1) - c.omega;
     const double f_tx = (lane0 ? u_t1 + kPi : u_t1) - t.omega;
     nd.f_cx = f_cx;
-    nd.r_ft = (t.a * (1.0 - e2_t)) / (1.0 + t.e * glibm::call::cos(f_tx));       // :363 / :365
+    nd.r_ft = (t.a * (1.0 - e2_t)) / (1.0 + t.e * Lm<EXACT>::cos(f_tx));       // :363 / :365
     const double one_m_e2 = 1.0 - e2_c;
     const double r_c = c.a * one_m_e2 / k;                                // :57
     const double p_c = c.a * one_m_e2;                                    // :58
     // rf_extreme_point, satellite_function.py:462-494 with fai = 0
     const double df = f_cx - c.f;
-    const double2 scdf = glibm::call::sincos(df);
+    const double2 scdf = Lm<EXACT>::sincos(df);
     const double sdf = scdf.x, cdf = scdf.y;
-    const double tmp1 = glibm::call::pow2(sdf) / (u_grav * k2 / (p_c * dv2) - 1.0);   // :466 / :481
+    const double tmp1 = Lm<EXACT>::pow2(sdf) / (u_grav * k2 / (p_c * dv2) - 1.0);   // :466 / :481
     if (!(0.0 <= tmp1)) { nd.status = 1; return; }                                    // :478 -> (0, 0)
     // :469-470 with tan(fai) = 0: beta = atan(+-0 / sdf) = +-0 for every finite non-zero sdf, so cos(beta) = 1 and the
     // subtracted term u k^2 sin(beta)^2 / p_c is +-0 (u k^2 finite, p_c non-zero): dvm = sqrt(dv^2) bit for bit. The general
@@ -423,17 +449,17 @@ SAT_DEV void dz_prepare(int craft, bool active, const double Ri[3], const double
         cb = 1.0;
         dvm = sqrt(dv2);
     } else {
-        const double2 scb = glibm::call::sincos(glibm::call::atan(0.0 / sdf));       // :469
+        const double2 scb = Lm<EXACT>::sincos(Lm<EXACT>::atan(0.0 / sdf));       // :469
         cb = scb.y;
-        dvm = sqrt(dv2 - u_grav * k2 * glibm::call::pow2(scb.x) / p_c);               // :470
+        dvm = sqrt(dv2 - u_grav * k2 * Lm<EXACT>::pow2(scb.x) / p_c);               // :470
     }
     // :464, :473-476 (theta stays 0 outside both ranges, Q5). One acos for the warp, the range decides how it is used:
     // an if / else-if around two acos calls made every warp run the routine twice with part of its lanes.
-    const double ac = glibm::call::acos(cdf * 1.0);
+    const double ac = Lm<EXACT>::acos(cdf * 1.0);
     const bool in_a = (-kTwoPi <= df && df < -kPi) || (0.0 <= df && df < kPi);
     const bool in_b = (-kPi <= df && df < 0.0) || (kPi <= df && df < kTwoPi);
     const double theta = in_a ? ac : (in_b ? kTwoPi - ac : 0.0);
-    const double2 scth = glibm::call::sincos(theta);
+    const double2 scth = Lm<EXACT>::sincos(theta);
     const double sth = scth.x, cth = scth.y;
     const double sq = sqrt(u_grav / p_c);
     const double sq_e_sin = sq * c.e * sf0;                                           // :518 first term
@@ -465,21 +491,23 @@ SAT_DEV double dz_guess(int j) { return (j == 0) ? kPi / 2 : -kPi / 2; }
 // evaluations (|f| == 0 exit). Exact shortcut; 45 % of the solves on env-visited states.
 SAT_DEV bool dz_degenerate(double A, double sth, double dvm) { return A == 0.0 && sth == 0.0 && fabs(dvm) <= 1.7976931348623157e308; }
 
+template <bool EXACT = true>
 SAT_DEV double dz_rf(const DzNode& nd, double alpha) {
-    const double2 sc = glibm::call::sincos(alpha);
+    const double2 sc = Lm<EXACT>::sincos(alpha);
     const double s = sc.x, c = sc.y;
     const double v1x = nd.sq_e_sin + nd.dvm * c;                                      // :525 / :541
     const double v1y = nd.sq_k + nd.dvm * s;                                          // :526 / :542
     const double hm = nd.r_c * v1y;
-    return fabs(glibm::call::pow2(hm) / (nd.u * (1.0 - nd.cth) + hm * v1y * nd.cth - hm * v1x * nd.sth));   // :530 / :545, :549-550
+    return fabs(Lm<EXACT>::pow2(hm) / (nd.u * (1.0 - nd.cth) + hm * v1y * nd.cth - hm * v1x * nd.sth));   // :530 / :545, :549-550
 }
 
 // returns 0/1/2, or -1 when the reference would raise; alpha0/alpha1 are ignored unless nd.status == 2
+template <bool EXACT = true>
 SAT_DEV int dz_finalize(bool active, const DzNode& nd, double alpha0, double alpha1, DzDebug* dbg) {
     int inside = 0;
     double rf_max = 0.0, rf_min = 0.0;
     if (nd.status == 2) {
-        const double r0 = dz_rf(nd, alpha0), r1 = dz_rf(nd, alpha1);
+        const double r0 = dz_rf<EXACT>(nd, alpha0), r1 = dz_rf<EXACT>(nd, alpha1);
         if (r0 < r1) { rf_max = r1; rf_min = r0; } else { rf_max = r0; rf_min = r1; }    // :551-554
     }
     if (nd.status >= 1) inside = (rf_min <= nd.r_ft && nd.r_ft <= rf_max) ? 1 : 0;        // :367-372

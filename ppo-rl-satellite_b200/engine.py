@@ -143,6 +143,7 @@ class EnvBatch:
                  d_range: float = 100000.0, fuel_c: float = 320.0, fuel_t: float = 320.0,
                  max_episode_steps: int = 1000, auto_reset: bool = True, substeps: int = 100, h: float = 1.0,
                  j2: float = J2, gamma: float = 0.99, skip_danger_zone: bool = False, t_step: float = 100.0,
+                 fast_libm: bool = False,
                  stm: np.ndarray | None = None, device="cuda"):
         torch = L.require_cuda()
         self.torch = torch
@@ -160,6 +161,7 @@ class EnvBatch:
         p.auto_reset = int(bool(auto_reset))
         p.substeps = int(substeps)
         p.skip_danger_zone = int(bool(skip_danger_zone))
+        p.fast_libm = int(bool(fast_libm))        # False: exact host-libm arithmetic in the danger-zone count (bit parity)
         p.d_capture, p.d_range, p.gamma = float(d_capture), float(d_range), float(gamma)
         p.h, p.j2 = float(h), float(j2)
         M = cw_stm(t_step) if stm is None else np.asarray(stm, dtype=np.float64)
