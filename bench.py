@@ -393,12 +393,22 @@ def run_config4(args, rank, world, dev, torch, dist, eng):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    # the same rollout with both actors' hidden layer on the tensor cores (opt-in variant, see config3_full_step)
+    agent.actor_kernel.use_tc = opp.actor_kernel.use_tc = True
+    e0.record(); tr.collect(); e1.record(); e1.synchronize()
+    ms_tc = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_tc, op=dist.ReduceOp.MAX)
+    ms_tc = float(ms_tc.item())
+    agent.actor_kernel.use_tc = opp.actor_kernel.use_tc = False
     out = {"what": "1 048 576 envs / %d GPUs = %d envs per GPU, rk4 mode (S=%d, J2 on), T=256 on-device rollout: 2 actor samplings + env "
                    "step per time step, transitions stored time-major; no collective; CUDA events around the rollout, max over ranks" % (world, n, args.substeps),
            "envs_total": total, "envs_per_gpu": n, "horizon": T, "rollout_ms": ms, "ms_per_step": ms / T,
            "env_steps_per_sec": total * T / (ms * 1e-3), "rk4_steps_per_sec": total * T / (ms * 1e-3) * 2 * args.substeps,
            "episodes_finished": int(tr.buf.done.sum().item()), "err_envs": int(env.err.sum().item()),
-           "rollout_buffer_gb_per_gpu": tr.buf.bytes_per_sample * T * n / 1e9}
+           "rollout_buffer_gb_per_gpu": tr.buf.bytes_per_sample * T * n / 1e9,
+           "tensor_core_actor_variant": {"rollout_ms": ms_tc, "ms_per_step": ms_tc / T, "env_steps_per_sec": total * T / (ms_tc * 1e-3),
+                                         "what": "same rollout, actors' hidden layer as 3xTF32 on tcgen05 (opt-in, not the default)"}}
     del tr, env, agent, opp
     torch.cuda.empty_cache()
     return out

@@ -213,12 +213,17 @@ GLIBM_FN double asin_poly(double z) {      // (((((f6 z + f5) z + f4) z + f3) z 
     return p;
 }
 
-// table ranges: ax = |x|, row at asncs[n] = {x_i, c1 .. c_deg, c_{deg+1}, asin(x_i) head, (unused here)}
+// table ranges: ax = |x|, row at asncs[n] = {x_i, c1 .. c_deg, c_{deg+1}, asin(x_i) head, (unused here)}. The six ranges of
+// e_asin.c differ only in the row width and the polynomial degree (6 .. 10), so they run through ONE code path: the Horner
+// recurrence starts at degree 10 with p = 0 and zero coefficients above `deg` - fma(0, xx, 0) = 0 and fma(0, xx, c_deg) = c_deg
+// exactly, so the bits are those of the degree-`deg` recurrence, and a warp whose lanes sit in different ranges does not
+// execute six copies of the routine.
 GLIBM_FN double acos_tab(double ax, int n, int deg, bool pos) {
     const double* T = glibm_asncs + n;
     const double xx = sub_(ax, T[0]);
-    double p = T[deg];
-    for (int j = deg - 1; j >= 2; --j) p = fma_(p, xx, T[j]);
+    double p = 0.0;
+#pragma unroll
+    for (int j = 10; j >= 2; --j) p = fma_(p, xx, (j <= deg) ? T[j] : 0.0);
     p = fma_(p, mul_(xx, xx), T[deg + 1]);
     const double t = fma_(xx, T[1], p);
     const double y = T[deg + 2];
@@ -238,12 +243,17 @@ GLIBM_FN double acos(double x) {
         return add_(r, fma_(neg_(p), mul_(x, x2), c0));
     }
     const double ax = pos ? x : neg_(x);
-    if (kk < 0x3fd00000) return acos_tab(ax, 11 * ((kk >> 15) & 0x1f), 6, pos);                 // < 0.25
-    if (kk < 0x3fe00000) return acos_tab(ax, 11 * ((kk >> 14) & 0x3f) + 352, 6, pos);           // < 0.5
-    if (kk < 0x3fe80000) return acos_tab(ax, 12 * ((kk >> 13) & 0x7f) + 1056, 7, pos);          // < 0.75
-    if (kk < 0x3fed8000) return acos_tab(ax, 13 * ((kk >> 13) & 0x7f) + 992, 8, pos);           // < 0.921875
-    if (kk < 0x3fee8000) return acos_tab(ax, 14 * ((kk >> 13) & 0x7f) + 884, 9, pos);           // < 0.953125
-    if (kk < 0x3fef0000) return acos_tab(ax, 15 * ((kk >> 13) & 0x7f) + 768, 10, pos);          // < 0.96875
+    if (kk < 0x3fef0000) {                                                   // 0.125 <= |x| < 0.96875: the six table ranges
+        const int i13 = (kk >> 13) & 0x7f;
+        int n, deg;
+        if (kk < 0x3fd00000) { n = 11 * ((kk >> 15) & 0x1f); deg = 6; }              // < 0.25
+        else if (kk < 0x3fe00000) { n = 11 * ((kk >> 14) & 0x3f) + 352; deg = 6; }   // < 0.5
+        else if (kk < 0x3fe80000) { n = 12 * i13 + 1056; deg = 7; }                  // < 0.75
+        else if (kk < 0x3fed8000) { n = 13 * i13 + 992; deg = 8; }                   // < 0.921875
+        else if (kk < 0x3fee8000) { n = 14 * i13 + 884; deg = 9; }                   // < 0.953125
+        else { n = 15 * i13 + 768; deg = 10; }                                       // < 0.96875
+        return acos_tab(ax, n, deg, pos);
+    }
     if (kk < 0x3ff00000) {                                                   // < 1: acos = 2 asin(sqrt((1 - |x|) / 2))
         const double z = mul_(pos ? sub_(1.0, x) : add_(x, 1.0), 0.5);
         const uint64_t v = bits_(z);
