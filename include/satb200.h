@@ -210,16 +210,23 @@ int sat_actor_sample(const SatActorWeights* w, const float* obs_f32, const SatEn
 
 /* Critic forward (ppo_continuous.py:123-128): v [n] = fc3(tanh(fc2(tanh(fc1(s))))).
  * w3/b3 are fc3.weight [1][hidden] / fc3.bias [1]; log_std unused. */
-/* The same sampling call with the 256 x 256 hidden layer on the tensor cores (csrc/actor_tc.cu): error-compensated 3xTF32
- * (every operand split into two TF32 words, three tcgen05.mma products accumulated in fp32 in TMEM), so the result carries
- * fp32-level accuracy like the reference's fp32 forward (ppo_continuous.py:83-95). Same arguments and Philox stream as
- * sat_actor_sample; tc_image is a caller-owned device scratch of SAT_ACTOR_TC_IMAGE_FLOATS floats (the pre-split, pre-swizzled
- * W2 operand; rebuilt from w->packed on every call, so it is never stale). sm_100a only. */
+/* The same sampling call with both dense layers on the tensor cores (csrc/actor_tc.cu): every fp32 operand is split exactly
+ * into three bf16 words and six tcgen05.mma products are accumulated in fp32 in TMEM (the exact 16-bit A_h B_h products in their
+ * own accumulator), so the result carries fp32-level accuracy like the reference's fp32 forward (ppo_continuous.py:83-95);
+ * tests/test_gpu_actor_tc.py holds its error against an fp64 ground truth at or below the FFMA path's. Same arguments and
+ * Philox stream as sat_actor_sample; tc_image is a caller-owned device scratch of SAT_ACTOR_TC_IMAGE_FLOATS floats (the
+ * pre-split, pre-swizzled weight operands; rebuilt from w->packed on every call, so it is never stale). sm_100a only.
+ * sat_actor_sample_pair_tc: two networks (same activation) on the same observations in ONE persistent launch, exactly the
+ * results of two sat_actor_sample_tc calls with steps step_a / step_b (the tensor-core form of sat_actor_sample_pair). */
 #define SAT_ACTOR_TC_IMAGE_FLOATS (2 * 256 * 256)
 int sat_actor_sample_tc(const SatActorWeights* w, float* tc_image, const float* obs_f32, const SatEnvState* st,
                         const double* obs_stats, int64_t n, int64_t row_offset, uint64_t seed, uint64_t step,
                         const float* eps_in, float* act, float* logp, float* mean_out, float* eps_out, float* obs_out,
                         void* stream);
+int sat_actor_sample_pair_tc(const SatActorWeights* wa, const SatActorWeights* wb, float* tc_image_a, float* tc_image_b,
+                             const float* obs_f32, const SatEnvState* st, const double* obs_stats, int64_t n, int64_t row_offset,
+                             uint64_t seed, uint64_t step_a, uint64_t step_b, float* act_a, float* logp_a, float* obs_out,
+                             float* act_b, float* logp_b, void* stream);
 int sat_critic_forward(const SatActorWeights* w, const float* obs_f32, int64_t n, float* v, void* stream);
 /* Two Gaussian actors on the same observations in ONE launch (pursuer and evader of a rollout step, CPPO_main.py:122-123):
  * exactly the results of two sat_actor_sample calls with steps step_a / step_b; obs_out (nullable) receives the fp32

@@ -50,32 +50,36 @@ constexpr int NCHUNK = NCH + 1;                 // + layer 1 (K = 18 padded to 3
 constexpr int NPART = 4;                        // threads per row
 constexpr int UPT = KC / NPART;                 // K values per thread per chunk: 8 = one 16-byte swizzle chunk
 constexpr int TC_COMPUTE = TM * NPART;          // 512
-constexpr int TC_THREADS = TC_COMPUTE + 32;
-constexpr int A_WORD = TM * 64;                 // one bf16 word (h, m or l) of an A chunk: 8 KB
-constexpr int A_STAGE = 3 * A_WORD;
-constexpr int B_WORD = HID * 64;                // 16 KB
-constexpr int B_STAGE = 3 * B_WORD;             // 48 KB
-constexpr int NSA = 2, NSB = 3;                 // ring depths
-constexpr int OFF_A = 0;
-constexpr int OFF_X = OFF_A + NSA * A_STAGE;    // the observation operand of the NEXT tile's layer 1 (written during this tile)
-constexpr int OFF_B = OFF_X + A_STAGE;
-constexpr int OFF_W3P = OFF_B + NSB * B_STAGE;  // float4 [HID]: (W3[0][c], W3[1][c], W3[2][c], b2[c])
-constexpr int OFF_B1P = OFF_W3P + HID * 16;     // b1 in layer-1 accumulator column order
-constexpr int OFF_BAR = OFF_B1P + HID * 4;      // mbarriers
-constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
+constexpr int TC_THREADS = TC_COMPUTE + 64;     // + the MMA-issue warp and the weight-stream warp
+constexpr int A_WORD = TM * 64;                 // one bf16 word (h, m or l) of an A chunk (32 k, SWIZZLE_64B rows): 8 KB
+constexpr int A_STAGE = 3 * A_WORD;             // 24 KB
+constexpr int NSUB = KC / 16;                   // weight sub-chunks (one UMMA k-step of 16) per chunk
+constexpr int B_WORD = HID * 32;                // one word of a weight sub-chunk (16 k, SWIZZLE_32B rows): 8 KB
+constexpr int B_STAGE = 3 * B_WORD;             // 24 KB
+constexpr int NSA = 4, NSB = 4;                 // ring depths
+constexpr int OFF_A = 0;                        // A ring: FIFO over the observation operand and the eight hidden chunks of every tile
+constexpr int OFF_B = OFF_A + NSA * A_STAGE;
+constexpr int OFF_RED = OFF_B + NSB * B_STAGE;  // head partial sums [2 tiles][NPART][TM] float4
+constexpr int OFF_W3P = OFF_RED + 2 * NPART * TM * 16;  // per column pair (a, b) two float4: (b2a', b2b', w0a, w0b), (w1a, w1b, w2a, w2b)
+constexpr int OFF_B1P = OFF_W3P + 2 * HID * 16; // b1 in layer-1 accumulator column order (both tables: one per network)
+constexpr int OFF_BAR = OFF_B1P + 2 * HID * 4;  // mbarriers
+constexpr int OFF_TMEM = OFF_BAR + 24 * 8;
 constexpr int TC_SMEM = OFF_TMEM + 16 + 1024;   // + slack for the 1024-byte alignment of the swizzled tiles
 static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
-static_assert(NPART * TM * 16 <= NSA * A_STAGE, "the head reduction scratch aliases the A ring");
-static_assert(NCHUNK * B_STAGE <= SAT_ACTOR_TC_IMAGE_FLOATS * 4, "weight image larger than the caller's scratch");
+static_assert(NCHUNK * NSUB * B_STAGE <= SAT_ACTOR_TC_IMAGE_FLOATS * 4, "weight image larger than the caller's scratch");
 constexpr uint32_t kTmemCols = 512;             // [0, 256): A_h B_h; [256, 512): the five small products
 // tcgen05 instruction descriptor (cute/arch/mma_sm100_desc.hpp, InstrDescriptor): D fp32 (1 << 4), A and B bf16 (1 << 7, 1 << 10),
 // both K-major (bits 15, 16 = 0), N = 256 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
-// shared-memory matrix descriptor of a K-major SWIZZLE_64B operand (64-byte rows) whose 8-row groups are 512 bytes apart
-// (SmemDescriptor: start >> 4, LBO = 1, SBO = 512 >> 4 at bit 32, version 1 at bit 46, layout type 4 at bit 61)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+// shared-memory matrix descriptors (SmemDescriptor: start >> 4, LBO = 1, SBO >> 4 at bit 32, version 1 at bit 46, layout type at
+// bit 61). A: K-major SWIZZLE_64B (64-byte rows, 8-row groups 512 bytes apart, type 4); B: K-major SWIZZLE_32B (32-byte rows =
+// exactly one UMMA k-step, 8-row groups 256 bytes apart, type 6)
+__device__ __forceinline__ uint64_t umma_desc_a(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc_b(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
@@ -90,6 +94,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // byte offset of (row, 16-byte chunk c16) inside one SWIZZLE_64B word buffer: Swizzle<2,4,3>, address bits [4,6) ^= bits [7,9)
 __host__ __device__ __forceinline__ uint32_t sw64(uint32_t row, uint32_t c16) {
     return row * 64u + (((c16 ^ (row >> 1)) & 3u) << 4);
+}
+// the same for SWIZZLE_32B (c16 in {0, 1}): Swizzle<1,4,3>, address bit 4 ^= bit 7
+__host__ __device__ __forceinline__ uint32_t sw32(uint32_t row, uint32_t c16) {
+    return row * 32u + (((c16 ^ (row >> 2)) & 1u) << 4);
 }
 // exact split of two fp32 values into bf16 words by truncation: v = h + m + l, every word has <= 8 significant bits
 // (h: the top 8 bits; v - h has <= 16, m its top 8; the rest has <= 8 and is a bf16 number). Packed as (v0 | v1 << 16).
@@ -106,30 +114,61 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& H, uint4& M, 
     split3(v[0], v[1], H.x, M.x, L.x); split3(v[2], v[3], H.y, M.y, L.y);
     split3(v[4], v[5], H.z, M.z, L.z); split3(v[6], v[7], H.w, M.w, L.w);
 }
-// tanh(x) = 1 - 2 / (exp(2x) + 1) on the two MUFU units, 5 instructions, abs. error ~1e-7 (inf / 0 saturate to +-1 by themselves)
-__device__ __forceinline__ float tanh5(float x) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    return fmaf(-2.0f, r, 1.0f);
-}
-template <bool TANH>
-__device__ __forceinline__ float act_fn(float x) { return TANH ? tanh5(x) : fmaxf(x, 0.0f); }
-
-// 32 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 16 consecutive accumulator columns, no wait (pair with tmem_wait())
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        "tcgen05.wait::ld.sync.aligned;"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// sum of the main and the small accumulator over the thread's 64 columns [c0, c0 + 64), 16 at a time (at most 32 transient registers)
+__device__ __forceinline__ void tmem_sum64(uint32_t lane_base, int c0, float (&sacc)[64]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float v[16], u[16];
+        tmem_ld16_nowait(lane_base + (uint32_t)(c0 + q * 16), v);
+        tmem_ld16_nowait(lane_base + (uint32_t)(HID + c0 + q * 16), u);
+        tmem_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sacc[q * 16 + j] = v[j] + u[j];
+    }
+}
+constexpr float kTwoLog2e = 2.8853900817779268f;
+// act() of two pre-activations on the packed fp32 pipe. TANH: tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1), the argument arrives
+// already multiplied by 2 log2(e)
+template <bool TANH>
+__device__ __forceinline__ float2 act2_scaled(float2 t) {
+    if (!TANH) return make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f));
+    float2 e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+    e = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
+    return __ffma2_rn(r, make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f));
+}
+
+// The same with the reciprocal on the packed FMA pipe (bit-trick seed + three Newton steps, ~1 ulp like rcp.approx): the epilogue
+// runs while the tensor core idles and two MUFU operations per value (16 per clock per SM) were its limit; this halves them.
+// The argument is clamped so that 2^t + 1 stays a normal number for the seed.
+template <bool TANH>
+__device__ __forceinline__ float2 act2_scaled_fma(float2 t) {
+    if (!TANH) return make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f));
+    float2 e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(fminf(t.x, 64.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(fminf(t.y, 64.0f)));
+    e = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+    r.x = __uint_as_float(0x7EF311C7u - __float_as_uint(e.x));
+    r.y = __uint_as_float(0x7EF311C7u - __float_as_uint(e.y));
+    const float2 ne = make_float2(-e.x, -e.y), one = make_float2(1.0f, 1.0f);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) r = __ffma2_rn(r, __ffma2_rn(ne, r, one), r);
+    return __ffma2_rn(r, make_float2(-2.0f, -2.0f), one);
 }
 
 // hidden unit held by layer-1 accumulator column c: thread quarter p = c >> 6 reads columns [64 p, 64 p + 64), and its value
@@ -137,13 +176,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 __host__ __device__ __forceinline__ int l1_unit(int c) { return ((c >> 3) & 7) * KC + (c >> 6) * UPT + (c & 7); }
 
 // The weight image: chunk 0 = W1 (n = layer-1 accumulator column, k = observation dimension, zero beyond 18), chunks 1..8 =
-// the K-chunks of W2 (n = output unit); per chunk [h | m | l] x 256 rows x 64 bytes (32 bf16 along k), 8-row groups of 512
-// bytes with the 16-byte column chunks XOR-swizzled: exactly the bytes the SWIZZLE_64B descriptor expects, so one linear 48 KB
-// bulk copy per chunk brings it in. packed: the FFMA kernel's image (W1T[k][j], W2T[k][n] = fc2.weight[n][k]).
-// One thread = 8 consecutive k of one n (coalesced over n).
-__global__ void actor_tc_pack_kernel(const float* __restrict__ packed, unsigned char* __restrict__ image) {
+// the K-chunks of W2 (n = output unit); every chunk is two sub-chunks of 16 k (one UMMA k-step), each [h | m | l] x 256 rows x
+// 32 bytes, 8-row groups of 256 bytes with the two 16-byte halves XOR-swizzled: exactly the bytes the SWIZZLE_32B descriptor
+// expects, so one linear 24 KB bulk copy per sub-chunk brings it in. packed: the FFMA kernel's image (W1T[k][j],
+// W2T[k][n] = fc2.weight[n][k]). One thread = 8 consecutive k of one n (coalesced over n).
+__global__ void actor_tc_pack_kernel(const float* __restrict__ packed0, unsigned char* __restrict__ image0,
+                                     const float* __restrict__ packed1, unsigned char* __restrict__ image1) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= NCHUNK * 4 * HID) return;
+    const float* __restrict__ packed = blockIdx.y ? packed1 : packed0;
+    unsigned char* __restrict__ image = blockIdx.y ? image1 : image0;
     const int n = idx % HID, c16 = (idx / HID) & 3, chunk = idx / (4 * HID);
     float v[8];
 #pragma unroll
@@ -154,11 +196,22 @@ __global__ void actor_tc_pack_kernel(const float* __restrict__ packed, unsigned 
     }
     uint4 H, M, L;
     split8(v, H, M, L);
-    unsigned char* base = image + (size_t)chunk * B_STAGE + sw64((uint32_t)n, (uint32_t)c16);
+    unsigned char* base = image + (size_t)(chunk * NSUB + (c16 >> 1)) * B_STAGE + sw32((uint32_t)n, (uint32_t)(c16 & 1));
     *reinterpret_cast<uint4*>(base) = H;
     *reinterpret_cast<uint4*>(base + B_WORD) = M;
     *reinterpret_cast<uint4*>(base + 2 * B_WORD) = L;
 }
+
+#ifdef SAT_TC_TRACE
+// tuning aid (never compiled into the shipped library): CTA 0 records %globaltimer at pipeline events
+__device__ unsigned long long g_tc_trace[2][256];
+__device__ __forceinline__ void tc_trace(int who, int slot) {
+    if (blockIdx.x == 0 && slot < 256) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_tc_trace[who][slot] = t; }
+}
+#define TC_TRACE(who, slot) tc_trace(who, slot)
+#else
+#define TC_TRACE(who, slot)
+#endif
 
 // the row's observation dimensions [8 part, 8 part + 8), split into the layer-1 A operand (one 16-byte chunk of each word buffer)
 __device__ __forceinline__ void produce_x(unsigned char* xs, uint32_t a_off, int part, int64_t g, bool live,
@@ -191,47 +244,73 @@ __device__ __forceinline__ void produce_x(unsigned char* xs, uint32_t a_off, int
     *reinterpret_cast<uint4*>(a0 + 2 * A_WORD) = L;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core
 }
+// L2 prefetch of what produce_x will read for row g (issued a tile ahead)
+__device__ __forceinline__ void prefetch_x(int part, int64_t g, int64_t n, const float* __restrict__ obs_f32, const SatEnvState& st) {
+    if (g >= n || part * UPT >= IN) return;
+    if (obs_f32) asm volatile("prefetch.global.L2 [%0];" ::"l"(obs_f32 + g * IN + part * UPT));
+    else {
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) {
+            const int k = part * UPT + j;
+            if (k < IN) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(st.state + (k < 6 ? k : k - 6) * st.ld + g));
+                if (k < 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(st.state + (k + 6) * st.ld + g));
+            }
+        }
+    }
+}
 // one arrival per warp once all its lanes are past their stores / TMEM loads
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 
-// Persistent: one CTA per SM walks over row tiles blockIdx.x, blockIdx.x + gridDim.x, ... The weight chunks stream through the
-// B ring continuously across tiles; the next tile's observation operand is produced while the last hidden-layer MMAs of the
-// current tile run, and its layer-1 MMAs start as soon as the epilogue has READ the accumulators (the epilogue arithmetic and
-// the sampling overlap them).
+// Persistent: one CTA per SM walks over row tiles blockIdx.x, blockIdx.x + gridDim.x, ... The weight sub-chunks stream through
+// the B ring continuously across tiles; the A ring is a FIFO over (observation operand, 8 hidden chunks) of successive tiles,
+// four stages deep, so the rows run up to four chunks ahead of the tensor core and the hand-off latency (stores, proxy fence,
+// mbarrier, MMA issue) is hidden; the next tile's observation operand is produced while the last hidden-layer MMAs of the
+// current tile run, and its layer-1 MMAs start as soon as the epilogue has the accumulators in registers.
+// one network of a launch: the pursuer's and the evader's actor of a rollout step (CPPO_main.py:122-123) run in ONE persistent
+// grid on the same observations (2 x ntiles tiles over the SMs instead of two launches with their own tails)
+struct TcNet {
+    const float* packed;
+    const unsigned char* image;
+    const float* eps_in;
+    float *act, *logp, *mean_out, *eps_out;
+    uint64_t step;
+    float max_action;
+};
+
 template <bool TANH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-actor_tc_kernel(const float* __restrict__ packed, const unsigned char* __restrict__ image, const float* __restrict__ obs_f32,
-                const SatEnvState st, const double* __restrict__ obs_stats, int64_t n, int64_t row_offset, uint64_t seed,
-                uint64_t step, float max_action, const float* __restrict__ eps_in, float* __restrict__ act,
-                float* __restrict__ logp, float* __restrict__ mean_out, float* __restrict__ eps_out, float* __restrict__ obs_out) {
+actor_tc_kernel(const __grid_constant__ TcNet net0, const __grid_constant__ TcNet net1, const int nnet,
+                const float* __restrict__ obs_f32, const SatEnvState st, const double* __restrict__ obs_stats, int64_t n,
+                int64_t row_offset, uint64_t seed, float* __restrict__ obs_out) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment for the swizzled tiles by pointer arithmetic on the shared array (an integer round trip would turn
     // every access into a generic-space LD/ST)
     unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     float4* w3p = reinterpret_cast<float4*>(sm + OFF_W3P);
     float* b1p = reinterpret_cast<float*>(sm + OFF_B1P);
+    float* red = reinterpret_cast<float*>(sm + OFF_RED);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
-    uint64_t* b_full = bars;          // [NSB] bulk copy of a weight chunk landed
-    uint64_t* b_empty = bars + 3;     // [NSB] the chunk's MMAs have read the B stage
-    uint64_t* a_full = bars + 6;      // [NSA] 128 rows of the A chunk written
-    uint64_t* a_empty = bars + 8;     // [NSA] the chunk's MMAs have read the A stage
-    uint64_t* x_full = bars + 10;     // the tile's observation operand written
-    uint64_t* l1_full = bars + 11;    // layer-1 accumulators complete
-    uint64_t* l1_read = bars + 12;    // every row has its layer-1 pre-activations in registers: the accumulators may be overwritten
-    uint64_t* l2_full = bars + 13;    // layer-2 accumulators complete
-    uint64_t* acc_free = bars + 14;   // the epilogue has read the accumulators: the next tile's layer 1 may start
+    uint64_t* b_full = bars;                  // [NSB] bulk copy of a weight sub-chunk landed
+    uint64_t* b_empty = bars + NSB;           // [NSB] the sub-chunk's MMAs have read the B stage
+    uint64_t* a_full = bars + 2 * NSB;        // [NSA] 128 rows of the A chunk written
+    uint64_t* a_empty = a_full + NSA;         // [NSA] the chunk's MMAs have read the A stage
+    uint64_t* l1_full = a_empty + NSA;        // layer-1 accumulators complete
+    uint64_t* l1_read = l1_full + 1;          // every row has its layer-1 pre-activations in registers: the accumulators may be overwritten
+    uint64_t* l2_full = l1_full + 2;          // layer-2 accumulators complete
+    uint64_t* acc_free = l1_full + 3;         // the epilogue has read the accumulators: the next tile's layer 1 may start
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int ntiles = (int)((n + TM - 1) / TM);
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // >= 1: gridDim.x <= ntiles
+    const int ntiles = (int)((n + TM - 1) / TM);                 // row tiles; work item u = net * ntiles + row tile
+    const int my_tiles = (ntiles * nnet - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // >= 1: gridDim.x <= ntiles * nnet
 
     if (tid == 0) {
         for (int s = 0; s < NSB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < NSA; ++s) { mbar_init(&a_full[s], TC_COMPUTE / 32); mbar_init(&a_empty[s], 1); }
-        mbar_init(x_full, TC_COMPUTE / 32); mbar_init(l1_full, 1); mbar_init(l1_read, TC_COMPUTE / 32);
+        mbar_init(l1_full, 1); mbar_init(l1_read, TC_COMPUTE / 32);
         mbar_init(l2_full, 1); mbar_init(acc_free, TC_COMPUTE / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -239,9 +318,18 @@ actor_tc_kernel(const float* __restrict__ packed, const unsigned char* __restric
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < HID; i += TC_THREADS) {
-        b1p[i] = packed[OFF_B1 + l1_unit(i)];
-        w3p[i] = make_float4(packed[OFF_W3 + i], packed[OFF_W3 + HID + i], packed[OFF_W3 + 2 * HID + i], packed[OFF_B2 + i]);
+    for (int i = tid; i < HID * nnet; i += TC_THREADS) {
+        // biases pre-multiplied by 2 log2(e) for the tanh networks (the activation takes its argument in that scale)
+        const int nt = i / HID, c = i % HID;
+        const float* pk = nt ? net1.packed : net0.packed;
+        const float bs = TANH ? kTwoLog2e : 1.0f;
+        b1p[nt * HID + c] = pk[OFF_B1 + l1_unit(c)] * bs;
+        const int pr = c >> 1, hb = c & 1;                                // column pair, which half
+        float* q0 = reinterpret_cast<float*>(w3p + nt * HID + 2 * pr);
+        q0[hb] = pk[OFF_B2 + c] * bs;
+        q0[2 + hb] = pk[OFF_W3 + c];
+        q0[4 + hb] = pk[OFF_W3 + HID + c];
+        q0[6 + hb] = pk[OFF_W3 + 2 * HID + c];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -249,59 +337,62 @@ actor_tc_kernel(const float* __restrict__ packed, const unsigned char* __restric
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == TC_COMPUTE / 32) {
-        // ------------------------------------------------------------------ control lane: weight stream + MMA issue
+        // ------------------------------------------------------------------ control lane: MMA issue
         if (tid == TC_COMPUTE) {
-            const int total_q = my_tiles * NCHUNK;                       // weight chunks this CTA consumes
-            for (int s = 0; s < NSB; ++s) {
-                mbar_expect_tx(&b_full[s], B_STAGE);
-                bulk_g2s(sm + OFF_B + s * B_STAGE, image + (size_t)s * B_STAGE, B_STAGE, &b_full[s]);
-            }
-            int q = 0, sb = 0, bphase = 0;                               // sb = q % NSB, bphase = (q / NSB) & 1
+            // (the weight stream is fed by warp 17, so this lane never waits for a refill and issues as far ahead as operands exist)
+            int sb = 0, bphase = 0;                                      // weight sub-chunk counter pq: sb = pq % NSB, bphase = (pq / NSB) & 1
+            int sa = 0, aphase = 0;                                      // A chunk counter qa = 9 t + c: sa = qa % NSA, aphase = (qa / NSA) & 1
 #pragma unroll 1
             for (int t = 0; t < my_tiles; ++t) {
 #pragma unroll 1
                 for (int c = 0; c < NCHUNK; ++c) {
-                    mbar_wait(&b_full[sb], bphase);
-                    uint32_t a_h;
-                    int sa = 0;
-                    if (c == 0) {
-                        mbar_wait(x_full, t & 1);
-                        if (t > 0) mbar_wait(acc_free, (t - 1) & 1);     // the previous tile's epilogue has read its accumulators
-                        a_h = smem_u32(sm + OFF_X);
-                    } else {
-                        const int qa = t * NCH + c - 1;
-                        sa = qa % NSA;
-                        mbar_wait(&a_full[sa], (qa / NSA) & 1);
-                        if (c == 1) mbar_wait(l1_read, t & 1);           // layer 2 starts over in the same accumulators
-                        a_h = smem_u32(sm + OFF_A + sa * A_STAGE);
-                    }
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_m = a_h + A_WORD, a_l = a_m + A_WORD;
-                    const uint32_t b_h = smem_u32(sm + OFF_B + sb * B_STAGE), b_m = b_h + B_WORD, b_l = b_m + B_WORD;
+                    TC_TRACE(0, (t * NCHUNK + c) * 3);
+                    mbar_wait(&a_full[sa], aphase);
+                    TC_TRACE(0, (t * NCHUNK + c) * 3 + 1);
+                    if (c == 0 && t > 0) mbar_wait(acc_free, (t - 1) & 1);   // the previous tile's epilogue has read its accumulators
+                    if (c == 1) mbar_wait(l1_read, t & 1);                   // layer 2 starts over in the same accumulators
+                    const uint32_t a_h = smem_u32(sm + OFF_A + sa * A_STAGE), a_m = a_h + A_WORD, a_l = a_m + A_WORD;
 #pragma unroll
-                    for (int ks = 0; ks < KC / 16; ++ks) {               // UMMA K = 16 bf16 = 32 bytes along the swizzled row
+                    for (int ks = 0; ks < NSUB; ++ks) {                  // UMMA K = 16 bf16 = 32 bytes along the swizzled A row
+                        mbar_wait(&b_full[sb], bphase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t b_h = smem_u32(sm + OFF_B + sb * B_STAGE), b_m = b_h + B_WORD, b_l = b_m + B_WORD;
                         const uint32_t o = ks * 32;
                         const uint32_t acc = (c <= 1 && ks == 0) ? 0u : 1u;
                         // smallest products first into the small accumulator, the exact 16-bit products alone into the main one
-                        umma_bf16(tmem_d + HID, umma_desc(a_m + o), umma_desc(b_m + o), acc);
-                        umma_bf16(tmem_d + HID, umma_desc(a_h + o), umma_desc(b_l + o), 1u);
-                        umma_bf16(tmem_d + HID, umma_desc(a_l + o), umma_desc(b_h + o), 1u);
-                        umma_bf16(tmem_d + HID, umma_desc(a_h + o), umma_desc(b_m + o), 1u);
-                        umma_bf16(tmem_d + HID, umma_desc(a_m + o), umma_desc(b_h + o), 1u);
-                        umma_bf16(tmem_d, umma_desc(a_h + o), umma_desc(b_h + o), acc);
+                        umma_bf16(tmem_d + HID, umma_desc_a(a_m + o), umma_desc_b(b_m), acc);
+                        umma_bf16(tmem_d + HID, umma_desc_a(a_h + o), umma_desc_b(b_l), 1u);
+                        umma_bf16(tmem_d + HID, umma_desc_a(a_l + o), umma_desc_b(b_h), 1u);
+                        umma_bf16(tmem_d + HID, umma_desc_a(a_h + o), umma_desc_b(b_m), 1u);
+                        umma_bf16(tmem_d + HID, umma_desc_a(a_m + o), umma_desc_b(b_h), 1u);
+                        umma_bf16(tmem_d, umma_desc_a(a_h + o), umma_desc_b(b_h), acc);
+                        umma_commit(&b_empty[sb]);                       // arrives when these MMAs have read their operands
+                        if (ks == NSUB - 1) {
+                            umma_commit(&a_empty[sa]);
+                            if (c == 0) umma_commit(l1_full);
+                            if (c == NCHUNK - 1) umma_commit(l2_full);
+                        }
+                        if (++sb == NSB) { sb = 0; bphase ^= 1; }
                     }
-                    if (c > 0) umma_commit(&a_empty[sa]);                // arrive when these MMAs have read their operands
-                    umma_commit(&b_empty[sb]);
-                    if (c == 0) umma_commit(l1_full);
-                    if (c == NCHUNK - 1) umma_commit(l2_full);
-                    // refill the B stage last used by chunk q - 1 with chunk q - 1 + NSB while chunk q computes
-                    if (q >= 1 && q - 1 + NSB < total_q) {
-                        const int so = (sb + NSB - 1) % NSB;
-                        mbar_wait(&b_empty[so], ((q - 1) / NSB) & 1);
-                        mbar_expect_tx(&b_full[so], B_STAGE);
-                        bulk_g2s(sm + OFF_B + so * B_STAGE, image + (size_t)((q - 1 + NSB) % NCHUNK) * B_STAGE, B_STAGE, &b_full[so]);
-                    }
-                    ++q;
+                    TC_TRACE(0, (t * NCHUNK + c) * 3 + 2);
+                    if (++sa == NSA) { sa = 0; aphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == TC_COMPUTE / 32 + 1) {
+        // ------------------------------------------------------------------ weight stream: 24 KB sub-chunks, W1 then W2, tile after tile
+        if (tid == TC_COMPUTE + 32) {
+            constexpr int SUBS = NCHUNK * NSUB;                          // weight sub-chunks per tile: 18
+            int sb = 0, bphase = 0, pq = 0;
+#pragma unroll 1
+            for (int t = 0; t < my_tiles; ++t) {
+                const int u = (int)blockIdx.x + t * (int)gridDim.x;
+                const unsigned char* img = (u >= ntiles) ? net1.image : net0.image;
+#pragma unroll 1
+                for (int idx = 0; idx < SUBS; ++idx, ++pq) {
+                    if (pq >= NSB) mbar_wait(&b_empty[sb], bphase ^ 1);  // the MMAs of sub-chunk pq - NSB have read this stage
+                    mbar_expect_tx(&b_full[sb], B_STAGE);
+                    bulk_g2s(sm + OFF_B + sb * B_STAGE, img + (size_t)idx * B_STAGE, B_STAGE, &b_full[sb]);
                     if (++sb == NSB) { sb = 0; bphase ^= 1; }
                 }
             }
@@ -312,115 +403,136 @@ actor_tc_kernel(const float* __restrict__ packed, const unsigned char* __restric
         const uint32_t a_off = sw64((uint32_t)r, (uint32_t)part);       // this thread's 16 bytes of every A word buffer
         const uint32_t lane_base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
         constexpr int CPT = HID / NPART;                                // accumulator columns per thread: 64
+        const float sc = TANH ? kTwoLog2e : 1.0f;
+        int sa = 0, aphase = 0, qa = 0;                                 // A chunk counter (same sequence as the control lane)
+        // work item t of this CTA: network and first row (network 1's tiles follow network 0's; the fp32 observation is written
+        // once, by network 0's tiles)
+        auto tile_net = [&](int tt) { return ((int)blockIdx.x + tt * (int)gridDim.x >= ntiles) ? 1 : 0; };
+        auto tile_row0 = [&](int tt) { const int u = (int)blockIdx.x + tt * (int)gridDim.x; return (int64_t)(u >= ntiles ? u - ntiles : u) * TM; };
         {
-            int64_t g = (int64_t)blockIdx.x * TM + r;
+            int64_t g = tile_row0(0) + r;
             const bool live = g < n;
-            produce_x(sm + OFF_X, a_off, part, live ? g : n - 1, live, obs_f32, st, obs_stats, obs_out);
-            warp_arrive(x_full);
+            produce_x(sm + OFF_A, a_off, part, live ? g : n - 1, live, obs_f32, st, obs_stats, tile_net(0) ? nullptr : obs_out);
+            warp_arrive(&a_full[0]);
+            sa = 1; qa = 1;
         }
+        // finishes action `part` of row r of tile tt from the four quarters' head partial sums: Philox sample, clamp, log-prob
+        auto sample_tile = [&](int tt) {
+            const int64_t g = tile_row0(tt) + r;
+            if (g >= n || part >= 3) return;
+            const int a = part;
+            const TcNet& nt = tile_net(tt) ? net1 : net0;
+            const float* __restrict__ packed = nt.packed;
+            const float* __restrict__ eps_in = nt.eps_in;
+            const uint64_t step = nt.step;
+            const float max_action = nt.max_action;
+            const float* rd = red + (tt & 1) * (NPART * TM * 4);
+            const float pre_a = ((rd[(0 * TM + r) * 4 + a] + rd[(1 * TM + r) * 4 + a]) + rd[(2 * TM + r) * 4 + a]) + rd[(3 * TM + r) * 4 + a];
+            float eps;
+            if (eps_in) eps = eps_in[g * 3 + a];
+            else {
+                const uint64_t gid = (uint64_t)(row_offset + g);
+                uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+                sat::philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+                // Box-Muller on (0,1) uniforms: (c0, c1) -> eps 0, 1; (c2, c3) -> eps 2 (same draws as actor.cu)
+                const uint32_t ca = (a == 2) ? c[2] : c[0], cb2 = (a == 2) ? c[3] : c[1];
+                const float ua = ((float)ca + 0.5f) * 2.3283064365386963e-10f, ub = ((float)cb2 + 0.5f) * 2.3283064365386963e-10f;
+                const float rr = sqrtf(-2.0f * logf(fminf(ua, 0.99999994f)));
+                float sn, cs;
+                sincosf(6.283185307179586f * ub, &sn, &cs);
+                eps = rr * ((a == 1) ? sn : cs);
+            }
+            const float mean = max_action * tanhf(pre_a + __ldg(packed + OFF_B3 + a));                        // :87
+            const float sd = expf(__ldg(packed + OFF_LS + a));                                               // :93
+            float xs = fmaf(sd, eps, mean);                                                                  // :186
+            xs = fminf(fmaxf(xs, -max_action), max_action);                                                  // :187
+            const float diff = xs - mean;
+            const float lp = -(diff * diff) / (2.0f * sd * sd) - logf(sd) - 0.9189385332046727f;             // :188
+            nt.act[g * 3 + a] = xs; nt.logp[g * 3 + a] = lp;
+            if (nt.mean_out) nt.mean_out[g * 3 + a] = mean;
+            if (nt.eps_out) nt.eps_out[g * 3 + a] = eps;
+        };
 #pragma unroll 1
         for (int t = 0; t < my_tiles; ++t) {
-            const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TM;
-            int64_t g = row0 + r;
-            const bool live = g < n;
-            if (!live) g = n - 1;
+            const int tab = tile_net(t) * HID;                          // this tile's bias / head tables
+            if (t + 1 < my_tiles) prefetch_x(part, tile_row0(t + 1) + r, n, obs_f32, st);
             // ---- layer-1 pre-activations of the thread's 64 hidden units (columns [64 part, +64) of both accumulators)
             float pre1[CPT];
+            if (tid == 0) TC_TRACE(1, t * 16);
             mbar_wait(l1_full, t & 1);
+            if (tid == 0) TC_TRACE(1, t * 16 + 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int cb = 0; cb < CPT / 32; ++cb) {
-                float v[32], u[32];
-                tmem_ld32(lane_base + (uint32_t)(part * CPT + cb * 32), v);
-                tmem_ld32(lane_base + (uint32_t)(HID + part * CPT + cb * 32), u);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) pre1[cb * 32 + j] = (v[j] + u[j]) + b1p[part * CPT + cb * 32 + j];
-            }
+            tmem_sum64(lane_base, part * CPT, pre1);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             warp_arrive(l1_read);
-            // ---- chunks 1..8: h1 = act(pre1), split, A operand of 32 hidden units
+            if (tid == 0) TC_TRACE(1, t * 16 + 2);
+            // ---- chunks 1..8: h1 = act(pre1 + b1), split, A operand of 32 hidden units
 #pragma unroll
             for (int kc = 0; kc < NCH; ++kc) {
-                const int qa = t * NCH + kc, sa = kc % NSA;             // NCH is a multiple of NSA
+                // the previous tile's sampling, where the rows are a full ring ahead of the tensor core (its head partial sums
+                // sit in the other half of the scratch; every thread is past its epilogue here)
+                if (kc == NSA && t > 0) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");   // the 16 compute warps only
+                    sample_tile(t - 1);
+                }
                 float h[UPT];
 #pragma unroll
-                for (int j = 0; j < UPT; ++j) h[j] = act_fn<TANH>(pre1[kc * UPT + j]);
+                for (int j = 0; j < UPT; j += 2) {
+                    const float2 bb = *reinterpret_cast<const float2*>(b1p + tab + part * CPT + kc * UPT + j);
+                    const float2 hh = act2_scaled<TANH>(__ffma2_rn(make_float2(pre1[kc * UPT + j], pre1[kc * UPT + j + 1]), make_float2(sc, sc), bb));
+                    h[j] = hh.x; h[j + 1] = hh.y;
+                }
                 uint4 H, M, L;
                 split8(h, H, M, L);
-                if (qa >= NSA) mbar_wait(&a_empty[sa], ((qa / NSA) - 1) & 1);   // the MMAs of A chunk qa - NSA have consumed this stage
+                if (qa >= NSA) mbar_wait(&a_empty[sa], aphase ^ 1);     // the MMAs of A chunk qa - NSA have consumed this stage
                 unsigned char* a0 = sm + OFF_A + sa * A_STAGE + a_off;
                 *reinterpret_cast<uint4*>(a0) = H;
                 *reinterpret_cast<uint4*>(a0 + A_WORD) = M;
                 *reinterpret_cast<uint4*>(a0 + 2 * A_WORD) = L;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 warp_arrive(&a_full[sa]);
+                if (tid == 0) TC_TRACE(1, t * 16 + 3 + kc);
+                ++qa;
+                if (++sa == NSA) { sa = 0; aphase ^= 1; }
             }
-            // ---- the next tile's observation operand, while the last chunks of this tile are on the tensor core (the layer-1
-            // MMAs that read the X stage completed before l1_full)
+            // ---- the next tile's observation operand goes into the ring behind this tile's last chunk
             if (t + 1 < my_tiles) {
-                int64_t gn = row0 + (int64_t)gridDim.x * TM + r;
+                int64_t gn = tile_row0(t + 1) + r;
                 const bool live_n = gn < n;
-                produce_x(sm + OFF_X, a_off, part, live_n ? gn : n - 1, live_n, obs_f32, st, obs_stats, obs_out);
-                warp_arrive(x_full);
+                if (qa >= NSA) mbar_wait(&a_empty[sa], aphase ^ 1);
+                produce_x(sm + OFF_A + sa * A_STAGE, a_off, part, live_n ? gn : n - 1, live_n, obs_f32, st, obs_stats,
+                          tile_net(t + 1) ? nullptr : obs_out);
+                warp_arrive(&a_full[sa]);
+                ++qa;
+                if (++sa == NSA) { sa = 0; aphase ^= 1; }
             }
 
-            // ------------------------------------------------------------------ epilogue: h2 = act(D + b2), heads, sample
+            // ------------------------------------------------------------------ epilogue: h2 = act(D + b2), head partial sums
+            if (tid == 0) TC_TRACE(1, t * 16 + 11);
             mbar_wait(l2_full, t & 1);
+            if (tid == 0) TC_TRACE(1, t * 16 + 12);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float pre[3] = {0.0f, 0.0f, 0.0f};
+            float acc2[CPT];
+            tmem_sum64(lane_base, part * CPT, acc2);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            warp_arrive(acc_free);                                       // accumulators are in registers: the next tile's layer 1 may run
+            if (tid == 0) TC_TRACE(1, t * 16 + 13);
+            float2 p0 = make_float2(0.0f, 0.0f), p1 = p0, p2 = p0;
 #pragma unroll
-            for (int cb = 0; cb < CPT / 32; ++cb) {
-                const int c0 = part * CPT + cb * 32;
-                float v[32], u[32];
-                tmem_ld32(lane_base + (uint32_t)c0, v);
-                tmem_ld32(lane_base + (uint32_t)(HID + c0), u);
-                if (cb == CPT / 32 - 1) {                                 // accumulators are in registers: release them
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    warp_arrive(acc_free);
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float4 wb = w3p[c0 + j];                        // (W3[0][col], W3[1][col], W3[2][col], b2[col]): one broadcast load
-                    const float h2 = act_fn<TANH>((v[j] + u[j]) + wb.w);
-                    pre[0] = fmaf(h2, wb.x, pre[0]); pre[1] = fmaf(h2, wb.y, pre[1]); pre[2] = fmaf(h2, wb.z, pre[2]);
-                }
+            for (int j = 0; j < CPT; j += 2) {
+                const float4 qa4 = w3p[tab + part * CPT + j], qb4 = w3p[tab + part * CPT + j + 1];   // pair (j, j + 1): two broadcast loads
+                const float2 h2 = act2_scaled_fma<TANH>(__ffma2_rn(make_float2(acc2[j], acc2[j + 1]), make_float2(sc, sc), make_float2(qa4.x, qa4.y)));
+                p0 = __ffma2_rn(h2, make_float2(qa4.z, qa4.w), p0);
+                p1 = __ffma2_rn(h2, make_float2(qb4.x, qb4.y), p1);
+                p2 = __ffma2_rn(h2, make_float2(qb4.z, qb4.w), p2);
             }
-            // reduce the four quarters of every row (all of this tile's MMAs are complete and the next tile's chunks are
-            // written by these same threads after the second barrier: the A ring is free to be used as scratch)
-            float* red = reinterpret_cast<float*>(sm + OFF_A);          // [NPART][TM][4]
-            *reinterpret_cast<float4*>(red + (part * TM + r) * 4) = make_float4(pre[0], pre[1], pre[2], 0.0f);
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");   // the 16 compute warps only
-            float pre_a = 0.0f;
-            if (part < 3)
-                pre_a = ((red[(0 * TM + r) * 4 + part] + red[(1 * TM + r) * 4 + part]) + red[(2 * TM + r) * 4 + part]) + red[(3 * TM + r) * 4 + part];
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
-            if (live && part < 3) {
-                const int a = part;
-                float eps;
-                if (eps_in) eps = eps_in[g * 3 + a];
-                else {
-                    const uint64_t gid = (uint64_t)(row_offset + g);
-                    uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
-                    sat::philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-                    // Box-Muller on (0,1) uniforms: (c0, c1) -> eps 0, 1; (c2, c3) -> eps 2 (same draws as actor.cu)
-                    const uint32_t ca = (a == 2) ? c[2] : c[0], cb2 = (a == 2) ? c[3] : c[1];
-                    const float ua = ((float)ca + 0.5f) * 2.3283064365386963e-10f, ub = ((float)cb2 + 0.5f) * 2.3283064365386963e-10f;
-                    const float rr = sqrtf(-2.0f * logf(fminf(ua, 0.99999994f)));
-                    float sn, cs;
-                    sincosf(6.283185307179586f * ub, &sn, &cs);
-                    eps = rr * ((a == 1) ? sn : cs);
-                }
-                const float mean = max_action * tanhf(pre_a + __ldg(packed + OFF_B3 + a));                        // :87
-                const float sd = expf(__ldg(packed + OFF_LS + a));                                               // :93
-                float xs = fmaf(sd, eps, mean);                                                                  // :186
-                xs = fminf(fmaxf(xs, -max_action), max_action);                                                  // :187
-                const float diff = xs - mean;
-                const float lp = -(diff * diff) / (2.0f * sd * sd) - logf(sd) - 0.9189385332046727f;             // :188
-                act[g * 3 + a] = xs; logp[g * 3 + a] = lp;
-                if (mean_out) mean_out[g * 3 + a] = mean;
-                if (eps_out) eps_out[g * 3 + a] = eps;
-            }
+            // the four quarters of every row meet in shared memory (double-buffered over tiles: the sampling of tile t runs
+            // during tile t + 1)
+            *reinterpret_cast<float4*>(red + (t & 1) * (NPART * TM * 4) + (part * TM + r) * 4) = make_float4(p0.x + p0.y, p1.x + p1.y, p2.x + p2.y, 0.0f);
+            if (tid == 0) TC_TRACE(1, t * 16 + 14);
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
+        sample_tile(my_tiles - 1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -436,51 +548,82 @@ inline int launch_status() {
 
 }  // namespace
 
+#ifdef SAT_TC_TRACE
+extern "C" int sat_debug_actor_tc_trace(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(g_tc_trace)); }
+#endif
+
+namespace {
+// launches the persistent kernel for one network (b == nullptr) or two networks on the same observations
+int launch_tc(const SatActorWeights* wa, float* image_a, const SatActorWeights* wb, float* image_b, const float* obs_f32,
+              const SatEnvState* st, const double* obs_stats, int64_t n, int64_t row_offset, uint64_t seed, uint64_t step_a,
+              uint64_t step_b, const float* eps_in, float* act_a, float* logp_a, float* mean_out, float* eps_out, float* obs_out,
+              float* act_b, float* logp_b, void* stream) {
+    const int nnet = wb ? 2 : 1;
+    if (!wa || !wa->packed || !image_a || !act_a || !logp_a || (!obs_f32 && !st)) return SAT_ERR_NULL;
+    if (wb && (!wb->packed || !image_b || !act_b || !logp_b)) return SAT_ERR_NULL;
+    if (wa->in_dim != IN || wa->hidden != HID || wa->act_dim != 3) return SAT_ERR_SIZE;
+    if (wb && (wb->in_dim != IN || wb->hidden != HID || wb->act_dim != 3)) return SAT_ERR_SIZE;
+    if (wb && (wb->use_tanh != 0) != (wa->use_tanh != 0)) return SAT_ERR_MODE;       // one activation per launch
+    if (n <= 0 || ((uintptr_t)wa->packed & 15) || ((uintptr_t)image_a & 15)) return SAT_ERR_SIZE;
+    if (wb && (((uintptr_t)wb->packed & 15) || ((uintptr_t)image_b & 15))) return SAT_ERR_SIZE;
+    if (!obs_f32 && (st->n < n || st->ld < st->n)) return SAT_ERR_SIZE;
+    static unsigned char done[64] = {0};
+    static int sm_count[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    const bool cached = dev >= 0 && dev < 64;
+    if (!cached || !done[dev]) {
+        e = cudaFuncSetAttribute(actor_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(actor_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        if (cached) done[dev] = 1;
+    }
+    int sms = cached ? sm_count[dev] : 0;
+    if (sms <= 0) {
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+        if (cached) sm_count[dev] = sms;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    // the images are rebuilt from the live weights on every call (a few microseconds): they can never be stale
+    TcNet n0 = {wa->packed, reinterpret_cast<unsigned char*>(image_a), eps_in, act_a, logp_a, mean_out, eps_out, step_a, wa->max_action};
+    TcNet n1 = n0;
+    if (wb) n1 = {wb->packed, reinterpret_cast<unsigned char*>(image_b), nullptr, act_b, logp_b, nullptr, nullptr, step_b, wb->max_action};
+    actor_tc_pack_kernel<<<dim3((NCHUNK * 4 * HID + 255) / 256, nnet), 256, 0, s>>>(n0.packed, const_cast<unsigned char*>(n0.image),
+                                                                                    n1.packed, const_cast<unsigned char*>(n1.image));
+    int rc = launch_status();
+    if (rc) return rc;
+    SatEnvState s0 = {};
+    if (!obs_f32) s0 = *st;
+    const int64_t work = ((n + TM - 1) / TM) * nnet;
+    const unsigned blocks = (unsigned)(work < sms ? work : sms);          // persistent: one CTA per SM walks over the tiles
+    if (wa->use_tanh)
+        actor_tc_kernel<true><<<blocks, TC_THREADS, TC_SMEM, s>>>(n0, n1, nnet, obs_f32, s0, obs_stats, n, row_offset, seed, obs_out);
+    else
+        actor_tc_kernel<false><<<blocks, TC_THREADS, TC_SMEM, s>>>(n0, n1, nnet, obs_f32, s0, obs_stats, n, row_offset, seed, obs_out);
+    return launch_status();
+}
+}  // namespace
+
 extern "C" {
 
 int sat_actor_sample_tc(const SatActorWeights* w, float* tc_image, const float* obs_f32, const SatEnvState* st,
                         const double* obs_stats, int64_t n, int64_t row_offset, uint64_t seed, uint64_t step,
                         const float* eps_in, float* act, float* logp, float* mean_out, float* eps_out, float* obs_out,
                         void* stream) {
-    if (!w || !w->packed || !tc_image || !act || !logp || (!obs_f32 && !st)) return SAT_ERR_NULL;
-    if (w->in_dim != IN || w->hidden != HID || w->act_dim != 3) return SAT_ERR_SIZE;
-    if (n <= 0 || ((uintptr_t)w->packed & 15) || ((uintptr_t)tc_image & 15)) return SAT_ERR_SIZE;
-    if (!obs_f32 && (st->n < n || st->ld < st->n)) return SAT_ERR_SIZE;
-    static unsigned char done[64] = {0};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return (int)e;
-    if (dev < 0 || dev >= 64 || !done[dev]) {
-        e = cudaFuncSetAttribute(actor_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(actor_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        if (dev >= 0 && dev < 64) done[dev] = 1;
-    }
-    cudaStream_t s = (cudaStream_t)stream;
-    // the image is rebuilt from the live weights on every call (9216 threads, a few microseconds): it can never be stale
-    unsigned char* image = reinterpret_cast<unsigned char*>(tc_image);
-    actor_tc_pack_kernel<<<(NCHUNK * 4 * HID + 255) / 256, 256, 0, s>>>(w->packed, image);
-    int rc = launch_status();
-    if (rc) return rc;
-    SatEnvState s0 = {};
-    if (!obs_f32) s0 = *st;
-    static int sm_count[64] = {0};
-    int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 0;
-    if (sms <= 0) {
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return (int)e;
-        if (dev >= 0 && dev < 64) sm_count[dev] = sms;
-    }
-    const int64_t ntiles = (n + TM - 1) / TM;
-    const unsigned blocks = (unsigned)(ntiles < sms ? ntiles : sms);      // persistent: one CTA per SM walks over the row tiles
-    if (w->use_tanh)
-        actor_tc_kernel<true><<<blocks, TC_THREADS, TC_SMEM, s>>>(w->packed, image, obs_f32, s0, obs_stats, n, row_offset, seed, step,
-                                                                  w->max_action, eps_in, act, logp, mean_out, eps_out, obs_out);
-    else
-        actor_tc_kernel<false><<<blocks, TC_THREADS, TC_SMEM, s>>>(w->packed, image, obs_f32, s0, obs_stats, n, row_offset, seed, step,
-                                                                   w->max_action, eps_in, act, logp, mean_out, eps_out, obs_out);
-    return launch_status();
+    return launch_tc(w, tc_image, nullptr, nullptr, obs_f32, st, obs_stats, n, row_offset, seed, step, 0, eps_in, act, logp,
+                     mean_out, eps_out, obs_out, nullptr, nullptr, stream);
+}
+
+int sat_actor_sample_pair_tc(const SatActorWeights* wa, const SatActorWeights* wb, float* tc_image_a, float* tc_image_b,
+                             const float* obs_f32, const SatEnvState* st, const double* obs_stats, int64_t n, int64_t row_offset,
+                             uint64_t seed, uint64_t step_a, uint64_t step_b, float* act_a, float* logp_a, float* obs_out,
+                             float* act_b, float* logp_b, void* stream) {
+    if (!wb) return SAT_ERR_NULL;
+    return launch_tc(wa, tc_image_a, wb, tc_image_b, obs_f32, st, obs_stats, n, row_offset, seed, step_a, step_b, nullptr, act_a,
+                     logp_a, nullptr, nullptr, obs_out, act_b, logp_b, stream);
 }
 
 }  // extern "C"

@@ -429,7 +429,9 @@ class GaussianActorKernel:
         self.use_tanh = int(bool(use_tanh))
         self._keep = None
         self.w = None
-        self.use_tc = os.environ.get("SAT_ACTOR_TC", "0") == "1"      # hidden layer on the tensor cores (3xTF32)
+        # both dense layers on the tensor cores (exact bf16x3 split, csrc/actor_tc.cu): the default; SAT_ACTOR_TC=0 or
+        # sample(tc=False) selects the fp32 FFMA2 kernel (csrc/actor.cu)
+        self.use_tc = os.environ.get("SAT_ACTOR_TC", "1") == "1"
         self._tc_image = None
 
     def load_state_dict(self, sd):
@@ -459,7 +461,7 @@ class GaussianActorKernel:
                step: int = 0, row_offset: int = 0, eps_in=None, act=None, logp=None, mean_out=None, eps_out=None,
                obs_out=None, tc: bool | None = None):
         """obs: CUDA fp32 [n,18]; or env=EnvBatch to read (and optionally normalise) the state directly.
-        tc: run the hidden layer as 3xTF32 on the tensor cores (sat_actor_sample_tc); default = self.use_tc."""
+        tc: run the dense layers as bf16x3 on the tensor cores (sat_actor_sample_tc); default = self.use_tc."""
         torch = self.torch
         L.guard_device(self.device)
         if self.w is None:
@@ -468,9 +470,7 @@ class GaussianActorKernel:
         act = torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device) if act is None else act
         logp = torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device) if logp is None else logp
         if (self.use_tc if tc is None else tc) and not self.critic:
-            if self._tc_image is None:
-                self._tc_image = torch.empty(L.ACTOR_TC_IMAGE_FLOATS, dtype=torch.float32, device=self.device)
-            L.check(self.lib.sat_actor_sample_tc(C.byref(self.w), self._tc_image.data_ptr(), L.ptr(obs),
+            L.check(self.lib.sat_actor_sample_tc(C.byref(self.w), self._image().data_ptr(), L.ptr(obs),
                                                  C.byref(env.st) if env is not None else None,
                                                  L.ptr(obs_stats.buf) if obs_stats is not None else None, n,
                                                  int(row_offset), int(seed) & (2 ** 64 - 1), int(step) & (2 ** 64 - 1),
@@ -484,24 +484,31 @@ class GaussianActorKernel:
                                           L.ptr(obs_out), L.stream_ptr()), "sat_actor_sample")
         return act, logp
 
+    def _image(self):
+        if self._tc_image is None:
+            self._tc_image = self.torch.empty(L.ACTOR_TC_IMAGE_FLOATS, dtype=self.torch.float32, device=self.device)
+        return self._tc_image
+
     def sample_pair(self, other, obs=None, env: EnvBatch | None = None, obs_stats: RunningStats | None = None,
                     seed: int = 0, step: int = 0, other_step: int = 1, row_offset: int = 0, act=None, logp=None,
-                    obs_out=None, other_act=None, other_logp=None):
+                    obs_out=None, other_act=None, other_logp=None, tc: bool | None = None):
         """this actor and `other` on the same observations: exactly self.sample(step=step) and
-        other.sample(step=other_step) -> (act, logp, other_act, other_logp). Up to 32 768 rows both networks go into ONE
-        launch (sat_actor_sample_pair) so that they share the GPU - measured one-launch / two-launch times: 4096 rows 44 / 75
-        us, 8192: 66 / 76, 32 768: 201 / 222; at 65 536 rows each network fills the GPU by itself (388 / 374) and two
-        launches are issued."""
+        other.sample(step=other_step) -> (act, logp, other_act, other_logp). Tensor-core path (default): both networks' row
+        tiles go through ONE persistent grid (sat_actor_sample_pair_tc) at any batch size. FFMA2 path (tc=False): up to 32 768
+        rows both networks go into one launch (sat_actor_sample_pair) so that they share the GPU - measured one-launch /
+        two-launch times: 4096 rows 44 / 75 us, 8192: 66 / 76, 32 768: 201 / 222; at 65 536 rows each network fills the GPU
+        by itself (388 / 374) and two launches are issued."""
         torch = self.torch
         L.guard_device(self.device)
         if self.w is None or other.w is None:
             raise L.SatError("weights not loaded")
         n = obs.shape[0] if obs is not None else env.n
-        if n > 32768:
+        use_tc = (self.use_tc if tc is None else tc) and not self.critic and not other.critic and self.use_tanh == other.use_tanh
+        if n > 32768 and not use_tc:
             act, logp = self.sample(obs=obs, env=env, obs_stats=obs_stats, seed=seed, step=step, row_offset=row_offset,
-                                    act=act, logp=logp, obs_out=obs_out)
+                                    act=act, logp=logp, obs_out=obs_out, tc=False)
             other_act, other_logp = other.sample(obs=obs, env=env, obs_stats=obs_stats, seed=seed, step=other_step,
-                                                 row_offset=row_offset, act=other_act, logp=other_logp)
+                                                 row_offset=row_offset, act=other_act, logp=other_logp, tc=False)
             return act, logp, other_act, other_logp
         new = lambda: torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device)
         act = new() if act is None else act
@@ -509,6 +516,16 @@ class GaussianActorKernel:
         other_act = new() if other_act is None else other_act
         other_logp = new() if other_logp is None else other_logp
         m64 = 2 ** 64 - 1
+        if use_tc:
+            # tensor-core path: both networks' row tiles share one persistent grid (any batch size)
+            L.check(self.lib.sat_actor_sample_pair_tc(C.byref(self.w), C.byref(other.w), self._image().data_ptr(),
+                                                      other._image().data_ptr(), L.ptr(obs),
+                                                      C.byref(env.st) if env is not None else None,
+                                                      L.ptr(obs_stats.buf) if obs_stats is not None else None, n,
+                                                      int(row_offset), int(seed) & m64, int(step) & m64, int(other_step) & m64,
+                                                      L.ptr(act), L.ptr(logp), L.ptr(obs_out), L.ptr(other_act),
+                                                      L.ptr(other_logp), L.stream_ptr()), "sat_actor_sample_pair_tc")
+            return act, logp, other_act, other_logp
         L.check(self.lib.sat_actor_sample_pair(C.byref(self.w), C.byref(other.w), L.ptr(obs),
                                                C.byref(env.st) if env is not None else None,
                                                L.ptr(obs_stats.buf) if obs_stats is not None else None, n, int(row_offset),

@@ -763,14 +763,15 @@ def test_step_timed_is_the_same_step(eng):
     assert torch.equal(a.state, b.state) and torch.equal(a.istate, b.istate)
 
 
-def test_actor_sample_pair_equals_two_calls(golden, eng):
-    """sat_actor_sample_pair: both networks in one launch, bit-identical to two sat_actor_sample calls"""
+@pytest.mark.parametrize("tc", [False, True])
+def test_actor_sample_pair_equals_two_calls(golden, eng, tc):
+    """sat_actor_sample_pair / sat_actor_sample_pair_tc: both networks in one launch, bit-identical to two single calls"""
     g = golden("ppo_golden.npz")
     W = _weights(g, "actor.")
     a = eng.GaussianActorKernel().load_state_dict(W)
     W2 = {k: (v * 0.9 + 0.01) for k, v in W.items()}
     b = eng.GaussianActorKernel().load_state_dict(W2)
-    for n in (1, 63, 1000):
+    for n in (1, 63, 1000, 20000):
         env = eng.EnvBatch(n, mode="cw")
         rng = np.random.default_rng(n)
         env.set_state(np.array([2e5, 0, 0]) + rng.normal(0, 3e4, (n, 3)), rng.normal(0, 3, (n, 3)),
@@ -778,9 +779,9 @@ def test_actor_sample_pair_equals_two_calls(golden, eng):
         stats = eng.RunningStats(18)
         stats.update_normalize(env.observe())
         obs1 = torch.empty((n, 18), dtype=torch.float32, device="cuda"); obs2 = torch.empty_like(obs1)
-        a1, l1 = a.sample(env=env, obs_stats=stats, seed=3, step=10, row_offset=7, obs_out=obs1)
-        b1, m1 = b.sample(env=env, obs_stats=stats, seed=3, step=11, row_offset=7)
-        a2, l2, b2, m2 = a.sample_pair(b, env=env, obs_stats=stats, seed=3, step=10, other_step=11, row_offset=7, obs_out=obs2)
+        a1, l1 = a.sample(env=env, obs_stats=stats, seed=3, step=10, row_offset=7, obs_out=obs1, tc=tc)
+        b1, m1 = b.sample(env=env, obs_stats=stats, seed=3, step=11, row_offset=7, tc=tc)
+        a2, l2, b2, m2 = a.sample_pair(b, env=env, obs_stats=stats, seed=3, step=10, other_step=11, row_offset=7, obs_out=obs2, tc=tc)
         for x, y in ((a1, a2), (l1, l2), (b1, b2), (m1, m2), (obs1, obs2)):
             assert torch.equal(x, y)
         assert not torch.equal(a1, b1)
