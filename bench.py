@@ -393,22 +393,24 @@ def run_config4(args, rank, world, dev, torch, dist, eng):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    # the same rollout with both actors' hidden layer on the tensor cores (opt-in variant, see config3_full_step)
-    agent.actor_kernel.use_tc = opp.actor_kernel.use_tc = True
-    e0.record(); tr.collect(); e1.record(); e1.synchronize()
-    ms_tc = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_tc, op=dist.ReduceOp.MAX)
-    ms_tc = float(ms_tc.item())
+    # the same rollout with the fp32 FFMA2 actor kernels (csrc/actor.cu; SAT_ACTOR_TC=0), see config3_full_step
+    tc_was = agent.actor_kernel.use_tc
     agent.actor_kernel.use_tc = opp.actor_kernel.use_tc = False
+    e0.record(); tr.collect(); e1.record(); e1.synchronize()
+    ms_ff = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_ff, op=dist.ReduceOp.MAX)
+    ms_ff = float(ms_ff.item())
+    agent.actor_kernel.use_tc = opp.actor_kernel.use_tc = tc_was
     out = {"what": "1 048 576 envs / %d GPUs = %d envs per GPU, rk4 mode (S=%d, J2 on), T=256 on-device rollout: 2 actor samplings + env "
                    "step per time step, transitions stored time-major; no collective; CUDA events around the rollout, max over ranks" % (world, n, args.substeps),
            "envs_total": total, "envs_per_gpu": n, "horizon": T, "rollout_ms": ms, "ms_per_step": ms / T,
            "env_steps_per_sec": total * T / (ms * 1e-3), "rk4_steps_per_sec": total * T / (ms * 1e-3) * 2 * args.substeps,
            "episodes_finished": int(tr.buf.done.sum().item()), "err_envs": int(env.err.sum().item()),
            "rollout_buffer_gb_per_gpu": tr.buf.bytes_per_sample * T * n / 1e9,
-           "tensor_core_actor_variant": {"rollout_ms": ms_tc, "ms_per_step": ms_tc / T, "env_steps_per_sec": total * T / (ms_tc * 1e-3),
-                                         "what": "same rollout, actors' hidden layer as 3xTF32 on tcgen05 (opt-in, not the default)"}}
+           "actors": "tensor cores (bf16x3, both networks in one persistent launch)" if tc_was else "fp32 FFMA2",
+           "ffma2_actor_variant": {"rollout_ms": ms_ff, "ms_per_step": ms_ff / T, "env_steps_per_sec": total * T / (ms_ff * 1e-3),
+                                   "what": "same rollout with the fp32 CUDA-core actor kernels (SAT_ACTOR_TC=0)"}}
     del tr, env, agent, opp
     torch.cuda.empty_cache()
     return out
@@ -468,12 +470,12 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     row_offset = rank * n
 
-    def full_step(t, tc=False):
+    def full_step(t, tc=None):
         k = t % RING
-        pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=t, row_offset=row_offset,
-                       act=buf_act[k], logp=buf_logp[k], obs_out=buf_obs[k], tc=tc)
-        evader.sample(env=env, obs_stats=obs_stats, seed=12, step=t, row_offset=row_offset,
-                      act=buf_eact[k], logp=buf_elogp[k], tc=tc)
+        # pursuer and evader act on the same observation (CPPO_main.py:122-123): one launch for both networks on the tensor-core
+        # path (the default), two FFMA2 launches at this batch size otherwise
+        pursuer.sample_pair(evader, env=env, obs_stats=obs_stats, seed=11, step=2 * t, other_step=2 * t + 1, row_offset=row_offset,
+                            act=buf_act[k], logp=buf_logp[k], obs_out=buf_obs[k], other_act=buf_eact[k], other_logp=buf_elogp[k], tc=tc)
         env.step(buf_act[k], buf_eact[k], reward=buf_rew[k], done=buf_done[k], obs_stats=obs_stats,
                  ret_stats=ret_stats, ret_std_out=buf_rstd[k:k + 1])
 
@@ -551,12 +553,14 @@ def run_ours(args, rank, world, local_rank):
     def _full():
         full_step(cnt[0]); cnt[0] += 1
     t_full, t_full_min = time_kernel(_full)
-    t_act, t_act_min = time_kernel(lambda: pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=0, act=buf_act[k], logp=buf_logp[k]))
-    # opt-in variant: the actors' hidden layer as 3xTF32 on the tensor cores (csrc/actor_tc.cu)
-    def _full_tc():
-        full_step(cnt[0], tc=True); cnt[0] += 1
-    t_full_tc, t_full_tc_min = time_kernel(_full_tc)
+    t_act, t_act_min = time_kernel(lambda: pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=0, act=buf_act[k], logp=buf_logp[k], tc=False))
+    # the fp32 FFMA2 actors (csrc/actor.cu) in the same step, and the tensor-core kernel alone (one network / the pair)
+    def _full_ff():
+        full_step(cnt[0], tc=False); cnt[0] += 1
+    t_full_ff, t_full_ff_min = time_kernel(_full_ff)
     t_act_tc, _ = time_kernel(lambda: pursuer.sample(env=env, obs_stats=obs_stats, seed=11, step=0, act=buf_act[k], logp=buf_logp[k], tc=True))
+    t_pair_tc, _ = time_kernel(lambda: pursuer.sample_pair(evader, env=env, obs_stats=obs_stats, seed=11, step=0, other_step=1, act=buf_act[k],
+                                                          logp=buf_logp[k], other_act=buf_eact[k], other_logp=buf_elogp[k], tc=True))
     # the same full step as 4 independent env shards ("virtual ranks": own running statistics, own stream) so that the
     # FP32 actor kernels of one shard overlap the FP64 env kernels of another
     def sharded_full_step_ms(parts_n=4, K=10):
@@ -686,7 +690,11 @@ def run_ours(args, rank, world, local_rank):
     ach_front = flop_step * n / (t_front * 1e-3) / 1e12
     traffic_front, traffic_front_src = ncu_traffic("env_front_rk4_kernel", n)
     traffic_finish, traffic_finish_src = ncu_traffic("env_step_kernel", n)
-    traffic_actor, traffic_actor_src = ncu_traffic("actor_kernel", n)
+    traffic_actor, traffic_actor_src = ncu_traffic("actor_tc_kernel_pair", n)
+    if os.path.exists(peaks_path) and "bf16_tflops_sustained" in json.load(open(peaks_path)):
+        bf16_peak, bf16_peak_src = json.load(open(peaks_path))["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step)"
+    else:
+        bf16_peak, bf16_peak_src = 2250.0, "nominal dense bf16 2.25 PFLOP/s (no MEASURED_PEAKS.json)"
     for c in gae_cases:
         for k_ in ("gae", "adv_moments", "adv_normalize"):
             c[k_ + "_frac_of_hbm_peak"] = c[k_ + "_gbs"] / hbm_peak
@@ -719,24 +727,32 @@ def run_ours(args, rank, world, local_rank):
                                     "hbm_achieved_gbs": BYTES_ENV_STEP * n / (t_env * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak}},
         # BASELINE config 3 exactly as worded ("full step ... with fused actor sampling"): both actors sample on the device, then the env step
         "config3_full_step": {
-            "what": "pursuer + evader fused Gaussian actor kernels (observation rebuilt + normalised from the fp64 state, Philox "
-                    "sampling, CPPO_main.py:122-123) + the env step above (:132); 5 launches; CUDA events, L2 flushed between steps",
+            "what": "pursuer + evader fused Gaussian actor sampling (observation rebuilt + normalised from the fp64 state, Philox "
+                    "sampling, CPPO_main.py:122-123; both networks in ONE persistent tensor-core launch, sat_actor_sample_pair_tc) + the env "
+                    "step above (:132); 5 launches (weight-image pack, actors, env front, env finish, statistics merge); CUDA events, L2 "
+                    "flushed between steps",
             "ms_per_step": t_full, "ms_per_step_min": t_full_min, "per_gpu_env_steps_per_sec": n / (t_full * 1e-3),
             "env_steps_per_sec": n * world / (t_full * 1e-3),
-            "split_ms": {"actor_x2": 2 * t_act, "env_front": t_front, "env_finish": t_finish, "stats_merge": t_merge},
-            "roofline": {"kernel": "actor_kernel<false> (fp32 FFMA2 register-tile MLP; 2 launches = %.0f %% of this step)" % (100 * 2 * t_act / t_full),
-                         "bound": "fp32", "achieved": ach_act, "peak": FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s",
-                         "frac": ach_act / FP32_NOMINAL_TFLOPS,
-                         "peak_source": "nominal FP32 pipe rate 148 SMs x 128 FFMA lanes x 2 x 1.965 GHz",
-                         "measured_ffma_chain_tflops": peak32, "frac_of_measured_chain": ach_act / peak32, "launch_ms": t_act,
+            "split_ms": {"actor_pair": t_pair_tc, "env_front": t_front, "env_finish": t_finish, "stats_merge": t_merge},
+            "roofline": {"kernel": "actor_tc_kernel (both dense layers of both actors as exact bf16x3 splits on tcgen05, accumulators in "
+                                   "TMEM; %.0f %% of this step)" % (100 * t_pair_tc / t_full),
+                         "bound": "tensor", "achieved": 6 * 2 * FLOP_ACTOR * n / (t_pair_tc * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                         "frac": 6 * 2 * FLOP_ACTOR * n / (t_pair_tc * 1e-3) / 1e12 / bf16_peak,
+                         "peak_source": bf16_peak_src,
+                         "what": "achieved = issued bf16 tensor FLOPs: 6 word products per fp32 product (exact 3-way split, 3 of 9 "
+                                 "products dropped at 2^-24) x the actor's 141 824 fp32 FLOP per row x 2 networks; useful fp32 rate = "
+                                 "achieved / 6",
+                         "useful_fp32_tflops": 2 * FLOP_ACTOR * n / (t_pair_tc * 1e-3) / 1e12,
+                         "launch_ms": t_pair_tc, "one_network_launch_ms": t_act_tc,
                          "traffic": traffic_actor, "traffic_source": traffic_actor_src},
-            "tensor_core_actor_variant": {
-                "what": "the same full step with both actors' 256 x 256 hidden layer on tcgen05 tensor cores (3xTF32, accumulators in TMEM; "
-                        "opt-in: GaussianActorKernel.sample(tc=True) / SAT_ACTOR_TC=1). Not the default: its error against an fp64 ground "
-                        "truth is 1.6x (tanh) / 2.0x (ReLU) the FFMA2 path's rms (tests/test_gpu_actor_tc.py); same Philox stream",
-                "ms_per_step": t_full_tc, "ms_per_step_min": t_full_tc_min, "per_gpu_env_steps_per_sec": n / (t_full_tc * 1e-3),
-                "actor_launch_ms": t_act_tc, "actor_speedup_vs_ffma2": t_act / t_act_tc,
-                "actor_useful_tflops": ach_act * t_act / t_act_tc},
+            "ffma2_actor_variant": {
+                "what": "the same full step with the fp32 CUDA-core actor kernels (actor_kernel<false>, FFMA2 register tiles; "
+                        "GaussianActorKernel.sample(tc=False) / SAT_ACTOR_TC=0): two launches at this batch size. Accuracy against an "
+                        "fp64 ground truth (tests/test_gpu_actor_tc.py): tensor-core path rms 6.5e-8 / FFMA2 7.2e-8 (tanh), 3.3e-8 / 3.5e-8 "
+                        "(ReLU); same Philox stream",
+                "ms_per_step": t_full_ff, "ms_per_step_min": t_full_ff_min, "per_gpu_env_steps_per_sec": n / (t_full_ff * 1e-3),
+                "actor_launch_ms": t_act, "actor_fp32_tflops": ach_act, "actor_frac_of_nominal_fp32": ach_act / FP32_NOMINAL_TFLOPS,
+                "tc_speedup_one_network": t_act / t_act_tc, "tc_speedup_pair": 2 * t_act / t_pair_tc},
             "as_4_independent_shards_on_4_streams": None if t_full4 is None else {
                 "ms_per_step": t_full4, "per_gpu_env_steps_per_sec": n / (t_full4 * 1e-3),
                 "what": "the same work as 4 env shards with per-shard running statistics on 4 streams: the FP32 actor kernels of "
