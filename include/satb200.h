@@ -104,6 +104,10 @@ int sat_env_init(const SatEnvState* st, double fuel_c, double fuel_t, const SatE
 int sat_env_reset(const SatEnvState* st, const uint8_t* mask, const SatEnvParams* p, void* stream);
 /* observation of the current state: [n][18] = [P-E, Pv-Ev, P, Pv, E, Ev] (environment.py:76-77) */
 int sat_env_observe(const SatEnvState* st, float* obs_f32, double* obs_f64, void* stream);
+/* The fp32 observation the policy networks are fed: rebuilt from the fp64 state (environment.py:76-77) and, when obs_stats !=
+ * NULL, normalised in fp64 with (x - mean)/(std + 1e-8) (Normalization.__call__ with update=False, normalization.py:37-43)
+ * before the cast - the arithmetic of sat_actor_sample's fused path, as one streaming kernel. */
+int sat_env_observe_norm(const SatEnvState* st, const double* obs_stats, float* obs_f32, void* stream);
 
 /* one step() for all envs.
  *   pa, ea          [n][3] pursuer / escaper actions (dtype per params)

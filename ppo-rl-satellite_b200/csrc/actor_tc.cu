@@ -216,33 +216,67 @@ __device__ __forceinline__ void tc_trace(int who, int slot) {
 // the row's observation dimensions [8 part, 8 part + 8), split into the layer-1 A operand (one 16-byte chunk of each word buffer)
 __device__ __forceinline__ void produce_x(unsigned char* xs, uint32_t a_off, int part, int64_t g, bool live,
                                           const float* __restrict__ obs_f32, const SatEnvState& st,
-                                          const double* __restrict__ obs_stats, float* __restrict__ obs_out) {
-    float xv[UPT];
+                                          const double* __restrict__ obs_stats, float (&xv)[UPT]) {
+    // all loads are issued before anything is computed (indices clamped instead of branching: the eight values' memory
+    // latencies overlap; with a branch per value they were paid one after the other, 7 us per tile on the state path)
+    const int k0 = part * UPT;
+    if (obs_f32) {
+        float v[UPT];
 #pragma unroll
-    for (int j = 0; j < UPT; ++j) {
-        const int k = part * UPT + j;
-        float val = 0.0f;
-        if (k < IN) {
-            if (obs_f32) val = obs_f32[g * IN + k];
-            else {
-                // rebuild the observation from the fp64 SoA env state (environment.py:76-77: P - E, Pv - Ev, P, Pv, E, Ev),
-                // normalise in fp64 (normalization.py:41)
-                const int64_t ld = st.ld;
-                double y = (k < 6) ? st.state[k * ld + g] - st.state[(k + 6) * ld + g] : st.state[(k - 6) * ld + g];
-                if (obs_stats) y = (y - obs_stats[1 + k]) / (obs_stats[1 + 2 * IN + k] + 1e-8);
-                val = (float)y;
+        for (int j = 0; j < UPT; ++j) v[j] = obs_f32[g * IN + (k0 + j < IN ? k0 + j : 0)];
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) xv[j] = (k0 + j < IN) ? v[j] : 0.0f;
+    } else {
+        // rebuild the observation from the fp64 SoA env state (environment.py:76-77: P - E, Pv - Ev, P, Pv, E, Ev), normalise in
+        // fp64 (normalization.py:41); columns: k < 6 -> state[k] - state[k + 6], else state[k - 6]
+        const int64_t ld = st.ld;
+#pragma unroll
+        for (int h = 0; h < UPT; h += 4) {
+            double ya[4], yb[4], mu[4], sd[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = (k0 + h + j < IN) ? k0 + h + j : 0;
+                ya[j] = st.state[(k < 6 ? k : k - 6) * ld + g];
+                yb[j] = st.state[(k < 6 ? k + 6 : k - 6) * ld + g];
+                mu[j] = obs_stats ? obs_stats[1 + k] : 0.0;
+                sd[j] = obs_stats ? obs_stats[1 + 2 * IN + k] : 0.0;
             }
-            if (obs_out && live) obs_out[g * IN + k] = val;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + h + j;
+                double y = (k < 6) ? ya[j] - yb[j] : ya[j];
+#ifdef SAT_TC_NODIV
+                if (obs_stats) y = (y - mu[j]) * (sd[j] + 1e-8);
+#else
+                if (obs_stats) y = (y - mu[j]) / (sd[j] + 1e-8);
+#endif
+                xv[h + j] = (k < IN) ? (float)y : 0.0f;
+            }
         }
-        xv[j] = val;
     }
+#ifdef SAT_TC_TRACE
+    if (threadIdx.x == 0 && xv[0] != 12345.678f) TC_TRACE(1, 200);
+#endif
     uint4 H, M, L;
     split8(xv, H, M, L);
     unsigned char* a0 = xs + a_off;
     *reinterpret_cast<uint4*>(a0) = H;
     *reinterpret_cast<uint4*>(a0 + A_WORD) = M;
     *reinterpret_cast<uint4*>(a0 + 2 * A_WORD) = L;
+#ifdef SAT_TC_TRACE
+    if (threadIdx.x == 0) TC_TRACE(1, 201);
+#endif
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core
+#ifdef SAT_TC_TRACE
+    if (threadIdx.x == 0) TC_TRACE(1, 202);
+#endif
+}
+// the fp32 observation actually fed to the network, written AFTER the operand hand-off: the proxy fence in produce_x is a
+// MEMBAR that would otherwise wait for these global stores
+__device__ __forceinline__ void store_obs(float* __restrict__ obs_out, int part, int64_t g, const float (&xv)[UPT]) {
+#pragma unroll
+    for (int j = 0; j < UPT; ++j)
+        if (part * UPT + j < IN) obs_out[g * IN + part * UPT + j] = xv[j];
 }
 // L2 prefetch of what produce_x will read for row g (issued a tile ahead)
 __device__ __forceinline__ void prefetch_x(int part, int64_t g, int64_t n, const float* __restrict__ obs_f32, const SatEnvState& st) {
@@ -412,8 +446,10 @@ actor_tc_kernel(const __grid_constant__ TcNet net0, const __grid_constant__ TcNe
         {
             int64_t g = tile_row0(0) + r;
             const bool live = g < n;
-            produce_x(sm + OFF_A, a_off, part, live ? g : n - 1, live, obs_f32, st, obs_stats, tile_net(0) ? nullptr : obs_out);
+            float xv[UPT];
+            produce_x(sm + OFF_A, a_off, part, live ? g : n - 1, live, obs_f32, st, obs_stats, xv);
             warp_arrive(&a_full[0]);
+            if (obs_out && live && !tile_net(0)) store_obs(obs_out, part, g, xv);
             sa = 1; qa = 1;
         }
         // finishes action `part` of row r of tile tt from the four quarters' head partial sums: Philox sample, clamp, log-prob
@@ -500,9 +536,12 @@ actor_tc_kernel(const __grid_constant__ TcNet net0, const __grid_constant__ TcNe
                 int64_t gn = tile_row0(t + 1) + r;
                 const bool live_n = gn < n;
                 if (qa >= NSA) mbar_wait(&a_empty[sa], aphase ^ 1);
-                produce_x(sm + OFF_A + sa * A_STAGE, a_off, part, live_n ? gn : n - 1, live_n, obs_f32, st, obs_stats,
-                          tile_net(t + 1) ? nullptr : obs_out);
+                if (tid == 0) TC_TRACE(1, t * 16 + 15);
+                if (tid == 0) TC_TRACE(1, 203);
+                float xv[UPT];
+                produce_x(sm + OFF_A + sa * A_STAGE, a_off, part, live_n ? gn : n - 1, live_n, obs_f32, st, obs_stats, xv);
                 warp_arrive(&a_full[sa]);
+                if (obs_out && live_n && !tile_net(t + 1)) store_obs(obs_out, part, gn, xv);
                 ++qa;
                 if (++sa == NSA) { sa = 0; aphase ^= 1; }
             }

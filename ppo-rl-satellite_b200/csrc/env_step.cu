@@ -702,6 +702,40 @@ __global__ void env_observe_kernel(const SatEnvState st, float* __restrict__ obs
 }
 
 
+// fp32 (normalised) observation for the policy networks: one thread per env reads its 12 state columns (coalesced over the
+// envs), the 18 values go through a shared-memory tile and leave as full rows. Same arithmetic as env_observe_kernel.
+constexpr int kObsNormEnvs = 128;
+__global__ void __launch_bounds__(kObsNormEnvs)
+env_observe_norm_kernel(const SatEnvState st, const double* __restrict__ obs_stats, float* __restrict__ obs_f32) {
+    __shared__ float tile[kObsNormEnvs * kObs];
+    const int64_t e0 = (int64_t)blockIdx.x * kObsNormEnvs;
+    const int64_t e = e0 + threadIdx.x;
+    const int64_t ld = st.ld;
+    if (e < st.n) {
+        double P[3], Pv[3], E[3], Ev[3], o[kObs];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            P[k] = st.state[(SAT_COL_P + k) * ld + e]; Pv[k] = st.state[(SAT_COL_PV + k) * ld + e];
+            E[k] = st.state[(SAT_COL_E + k) * ld + e]; Ev[k] = st.state[(SAT_COL_EV + k) * ld + e];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            o[k] = __dsub_rn(P[k], E[k]); o[3 + k] = __dsub_rn(Pv[k], Ev[k]);
+            o[6 + k] = P[k]; o[9 + k] = Pv[k]; o[12 + k] = E[k]; o[15 + k] = Ev[k];
+        }
+#pragma unroll
+        for (int j = 0; j < kObs; ++j) {
+            double v = o[j];
+            if (obs_stats) v = (v - obs_stats[1 + j]) / (obs_stats[1 + 2 * kObs + j] + 1e-8);
+            tile[threadIdx.x * kObs + j] = (float)v;
+        }
+    }
+    __syncthreads();
+    const int64_t rem = st.n - e0;
+    const int total = (int)(rem < kObsNormEnvs ? rem : kObsNormEnvs) * kObs;
+    for (int idx = threadIdx.x; idx < total; idx += kObsNormEnvs) obs_f32[e0 * kObs + idx] = tile[idx];
+}
+
 // ---------------------------------------------------------------------------------------------
 // stand-alone batch normalisation (Normalization.__call__, normalization.py:37-43)
 // ---------------------------------------------------------------------------------------------
@@ -798,6 +832,15 @@ int sat_env_reset(const SatEnvState* st, const uint8_t* mask, const SatEnvParams
     const int threads = 256;
     const unsigned blocks = (unsigned)((st->n + threads - 1) / threads);
     env_init_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(*st, 0.0, 0.0, *p, mask, 0);
+    return launch_status();
+}
+
+int sat_env_observe_norm(const SatEnvState* st, const double* obs_stats, float* obs_f32, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!obs_f32) return SAT_ERR_NULL;
+    const unsigned blocks = (unsigned)((st->n + kObsNormEnvs - 1) / kObsNormEnvs);
+    env_observe_norm_kernel<<<blocks, kObsNormEnvs, 0, (cudaStream_t)stream>>>(*st, obs_stats, obs_f32);
     return launch_status();
 }
 

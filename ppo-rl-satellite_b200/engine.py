@@ -470,6 +470,8 @@ class GaussianActorKernel:
         act = torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device) if act is None else act
         logp = torch.empty((n, ACT_DIM), dtype=torch.float32, device=self.device) if logp is None else logp
         if (self.use_tc if tc is None else tc) and not self.critic:
+            if obs is None:
+                obs, env, obs_stats, obs_out = self._tc_obs(env, obs_stats, obs_out), None, None, None
             L.check(self.lib.sat_actor_sample_tc(C.byref(self.w), self._image().data_ptr(), L.ptr(obs),
                                                  C.byref(env.st) if env is not None else None,
                                                  L.ptr(obs_stats.buf) if obs_stats is not None else None, n,
@@ -483,6 +485,19 @@ class GaussianActorKernel:
                                           L.ptr(eps_in), L.ptr(act), L.ptr(logp), L.ptr(mean_out), L.ptr(eps_out),
                                           L.ptr(obs_out), L.stream_ptr()), "sat_actor_sample")
         return act, logp
+
+    def _tc_obs(self, env, obs_stats, obs_out):
+        """tensor-core path on the env state: the fp32 (normalised) observation is materialised by one streaming kernel
+        (sat_env_observe_norm, the fused path's arithmetic) into obs_out / a cached scratch and the GEMM kernel reads that:
+        rebuilding it inside the kernel cost the row warps 4.6 us per 128-row tile (fp64 loads + divisions on 8 of 16 warps)."""
+        n = env.n
+        if obs_out is None:
+            if getattr(self, "_obs_scratch", None) is None or self._obs_scratch.shape[0] < n:
+                self._obs_scratch = self.torch.empty((n, OBS_DIM), dtype=self.torch.float32, device=self.device)
+            obs_out = self._obs_scratch[:n]
+        L.check(self.lib.sat_env_observe_norm(C.byref(env.st), L.ptr(obs_stats.buf) if obs_stats is not None else None,
+                                              L.ptr(obs_out), L.stream_ptr()), "sat_env_observe_norm")
+        return obs_out
 
     def _image(self):
         if self._tc_image is None:
@@ -518,6 +533,8 @@ class GaussianActorKernel:
         m64 = 2 ** 64 - 1
         if use_tc:
             # tensor-core path: both networks' row tiles share one persistent grid (any batch size)
+            if obs is None:
+                obs, env, obs_stats, obs_out = self._tc_obs(env, obs_stats, obs_out), None, None, None
             L.check(self.lib.sat_actor_sample_pair_tc(C.byref(self.w), C.byref(other.w), self._image().data_ptr(),
                                                       other._image().data_ptr(), L.ptr(obs),
                                                       C.byref(env.st) if env is not None else None,

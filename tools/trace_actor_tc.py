@@ -7,8 +7,16 @@ import bench
 n = 65536
 actor = eng.GaussianActorKernel().load_state_dict(bench.orthogonal_actor_state(torch, 0))
 x = torch.randn((n, 18), device="cuda")
+if os.environ.get("SAT_TRACE_STATE", "0") == "1":
+    env = eng.EnvBatch(n, mode="rk4", substeps=100, h=1.0, d_capture=20000.0, max_episode_steps=1000)
+    rng = np.random.default_rng(1)
+    env.set_state(np.array([2e5, 0, 0]) + rng.normal(0, 3e4, (n, 3)), rng.normal(0, 3, (n, 3)), np.array([1.8e4, 0, 0]) + rng.normal(0, 3e4, (n, 3)), rng.normal(0, 3, (n, 3)))
+    st = eng.RunningStats(18); st.update_normalize(env.observe())
+    kw = dict(env=env, obs_stats=st, obs_out=x)
+else:
+    kw = dict(obs=x)
 for i in range(5):
-    actor.sample(obs=x, seed=1, step=i, tc=True)
+    actor.sample(seed=1, step=i, tc=True, **kw)
 torch.cuda.synchronize()
 lib = L.load()
 buf = (C.c_ulonglong * 512)()
@@ -26,4 +34,5 @@ for tile in range(4):
 names = ["pre-l1_full", "l1_full", "R done"] + [f"chunk{k} arrived" for k in range(1, 9)] + ["pre-l2_full", "l2_full", "acc_free", "tile end"]
 print("compute thread 0:")
 for tile in range(4):
-    print("  tile", tile, " ".join(f"{names[j]}={cmp_[tile*16+j]:.2f}" for j in range(15)))
+    print("  tile", tile, " ".join(f"{names[j]}={cmp_[tile*16+j]:.2f}" for j in range(15)), f"X stage free={cmp_[tile*16+15]:.2f}")
+print("last X production: stage free %.2f, values ready %.2f, stored %.2f, fenced %.2f" % (cmp_[203], cmp_[200], cmp_[201], cmp_[202]))
