@@ -310,6 +310,10 @@ typedef struct SatPpoNet {
     int32_t reserved;
 } SatPpoNet;
 
+/* Forward / backward kernel of sat_ppo_actor_grad / sat_ppo_critic_grad: tensor cores (csrc/ppo_fb_tc.cu: the three 256-wide
+ * contractions per row tile as exact bf16x3 splits on tcgen05, fp32-level accuracy; the default) or the fp32 FFMA2 kernel
+ * (enable = 0, or SAT_PPO_TC=0 in the environment). enable < 0 only queries. Returns the previous setting. Process-wide. */
+int sat_ppo_use_tensor_cores(int enable);
 int64_t sat_ppo_workspace_floats(int64_t mb);
 /* rebuild `packed` from `params` (after loading a checkpoint into the torch views) */
 int sat_ppo_pack(const SatPpoNet* net, void* stream);

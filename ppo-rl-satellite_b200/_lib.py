@@ -67,6 +67,7 @@ SIGNATURES = {
     "sat_state_eq": (C.c_int, [_P, _P, _I64, _I64, _D, _D, _D, _P]),
     "sat_cw_propagate": (C.c_int, [_P, _I64, _I64, C.POINTER(C.c_double), _P]),
     "sat_cw_ode_rk45": (C.c_int, [_P, _I64, _I64, _D, _D, _D, _D, _D, _D, _P, _P]),
+    "sat_ppo_use_tensor_cores": (C.c_int, [C.c_int]),
     "sat_ppo_workspace_floats": (C.c_int64, [_I64]),
     "sat_ppo_pack": (C.c_int, [_P, _P]),
     "sat_ppo_actor_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _P]),

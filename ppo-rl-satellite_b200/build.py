@@ -31,6 +31,7 @@ UNITS = {
     "actor.cu": [],
     "actor_tc.cu": [],
     "ppo_update.cu": [],
+    "ppo_fb_tc.cu": [],
     "capi.cu": [],
 }
 

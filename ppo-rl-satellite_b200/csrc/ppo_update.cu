@@ -21,6 +21,8 @@
 //                     (transposed) weight image for the next forward.
 #include <cooperative_groups.h>
 #include "mlp_tile.cuh"
+#include "ppo_fb_tc.cuh"
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -37,16 +39,18 @@ __host__ __device__ inline int param_floats(int heads) { return SAT_PPO_PARAM_FL
 
 struct Workspace {
     float *h1, *dz2b, *dz1, *xs, *part_head, *part_scal, *part_w2, *part_w1, *part_b1;
+    unsigned char* tc_image;         // the tensor-core forward/backward kernel's split, swizzled weight operands
     int64_t mp, tiles;
 };
+constexpr int64_t MP_ALIGN = 128;    // rows are padded to the tensor-core kernel's 128-row tile (two 64-row FFMA tiles)
 __host__ inline int64_t ws_floats(int64_t mb) {
-    const int64_t mp = (mb + M - 1) / M * M, tiles = mp / M;
+    const int64_t mp = (mb + MP_ALIGN - 1) / MP_ALIGN * MP_ALIGN, tiles = mp / M;
     return mp * HID * 3 + mp * XS_LD + tiles * 4 * HID + tiles * 8 + (int64_t)W2_SLABS * HID * HID +
-           (int64_t)W1_SLABS * (HID * IN + HID);
+           (int64_t)W1_SLABS * (HID * IN + HID) + SAT_PPO_TC_IMAGE_BYTES / 4 + 64;
 }
 __host__ inline Workspace ws_carve(float* base, int64_t mb) {
     Workspace w;
-    w.mp = (mb + M - 1) / M * M; w.tiles = w.mp / M;
+    w.mp = (mb + MP_ALIGN - 1) / MP_ALIGN * MP_ALIGN; w.tiles = w.mp / M;
     float* p = base;
     w.h1 = p; p += w.mp * HID;
     w.dz2b = p; p += w.mp * HID;
@@ -56,7 +60,8 @@ __host__ inline Workspace ws_carve(float* base, int64_t mb) {
     w.part_scal = p; p += w.tiles * 8;
     w.part_w2 = p; p += (int64_t)W2_SLABS * HID * HID;
     w.part_w1 = p; p += (int64_t)W1_SLABS * HID * IN;
-    w.part_b1 = p;
+    w.part_b1 = p; p += (int64_t)W1_SLABS * HID;
+    w.tc_image = reinterpret_cast<unsigned char*>(p + ((64 - ((p - base) & 63)) & 63));     // 256-byte aligned (base is 16-byte aligned)
     return w;
 }
 
@@ -636,7 +641,7 @@ int check_net(const SatPpoNet* net) {
 }
 
 // everything after the forward/backward kernel: weight-gradient kernels and the partial sums
-int finish_grads(const SatPpoNet* net, const Workspace& w, cudaStream_t stream) {
+int finish_grads(const SatPpoNet* net, const Workspace& w, cudaStream_t stream, int64_t head_tiles) {
     const int heads = net->heads;
     const int64_t ktiles = w.mp / KT;
     const int slabs2 = (int)(ktiles < W2_SLABS ? ktiles : W2_SLABS);
@@ -656,17 +661,31 @@ int finish_grads(const SatPpoNet* net, const Workspace& w, cudaStream_t stream) 
     add(w.part_w2, (int64_t)HID * HID, slabs2, HID * HID, SAT_PPO_OFF_W2);
     add(w.part_w1, (int64_t)HID * IN, slabs1, HID * IN, SAT_PPO_OFF_W1);
     add(w.part_b1, HID, slabs1, HID, SAT_PPO_OFF_B1);
-    add(w.part_head, 4 * HID, (int)w.tiles, heads * HID, SAT_PPO_OFF_W3);
-    add(w.part_head + 3 * HID, 4 * HID, (int)w.tiles, HID, SAT_PPO_OFF_B2);
-    add(w.part_scal, 8, (int)w.tiles, heads == 3 ? 7 : 2, off_b3(heads));        // db3, dlog_std, loss (one past the parameters)
+    add(w.part_head, 4 * HID, (int)head_tiles, heads * HID, SAT_PPO_OFF_W3);
+    add(w.part_head + 3 * HID, 4 * HID, (int)head_tiles, HID, SAT_PPO_OFF_B2);
+    add(w.part_scal, 8, (int)head_tiles, heads == 3 ? 7 : 2, off_b3(heads));        // db3, dlog_std, loss (one past the parameters)
     plan.groups = gi;
     colsum_kernel<<<nb, 1024, 0, stream>>>(plan, net->grads);
     return launch_status();
 }
 
+// forward / backward kernel: tensor cores (ppo_fb_tc.cu, default) or fp32 FFMA2 (ppo_fb_kernel); SAT_PPO_TC=0 or
+// sat_ppo_use_tensor_cores(0) selects the latter
+int g_ppo_tc = -1;
+inline bool ppo_tc_enabled() {
+    if (g_ppo_tc < 0) { const char* e = std::getenv("SAT_PPO_TC"); g_ppo_tc = (e && e[0] == '0') ? 0 : 1; }
+    return g_ppo_tc != 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int sat_ppo_use_tensor_cores(int enable) {
+    const int prev = ppo_tc_enabled() ? 1 : 0;
+    if (enable >= 0) g_ppo_tc = enable ? 1 : 0;
+    return prev;
+}
 
 int64_t sat_ppo_workspace_floats(int64_t mb) { return mb > 0 ? ws_floats(mb) : 0; }
 
@@ -687,12 +706,19 @@ int sat_ppo_actor_grad(const SatPpoNet* net, const float* s, const float* a, con
     rc = set_smem(ppo_fb_kernel<false>, sizeof(FbSmem));
     if (rc) return rc;
     const Workspace w = ws_carve(net->workspace, mb);
+    if (ppo_tc_enabled()) {
+        rc = ppo_fb_tc_launch(false, net->use_tanh != 0, net->packed, w.tc_image, net->max_action, s, a, old_logp, adv, nullptr, index, mb,
+                              1.0f / (float)mb, epsilon, entropy_coef, w.h1, w.dz2b, w.dz1, w.xs, w.part_head, w.part_scal, w.mp,
+                              (cudaStream_t)stream);
+        if (rc) return rc;
+        return finish_grads(net, w, (cudaStream_t)stream, w.mp / MP_ALIGN);
+    }
     ppo_fb_kernel<false><<<(unsigned)w.tiles, THREADS, sizeof(FbSmem), (cudaStream_t)stream>>>(
         net->packed, net->params + SAT_PPO_OFF_W2, net->use_tanh, net->max_action, s, a, old_logp, adv, nullptr, index, mb,
         1.0f / (float)mb, epsilon, entropy_coef, w.h1, w.dz2b, w.dz1, w.xs, w.part_head, w.part_scal, w.mp);
     rc = launch_status();
     if (rc) return rc;
-    return finish_grads(net, w, (cudaStream_t)stream);
+    return finish_grads(net, w, (cudaStream_t)stream, w.tiles);
 }
 
 int sat_ppo_critic_grad(const SatPpoNet* net, const float* s, const float* v_target, const int64_t* index, int64_t mb,
@@ -704,12 +730,19 @@ int sat_ppo_critic_grad(const SatPpoNet* net, const float* s, const float* v_tar
     rc = set_smem(ppo_fb_kernel<true>, sizeof(FbSmem));
     if (rc) return rc;
     const Workspace w = ws_carve(net->workspace, mb);
+    if (ppo_tc_enabled()) {
+        rc = ppo_fb_tc_launch(true, net->use_tanh != 0, net->packed, w.tc_image, 0.0f, s, nullptr, nullptr, nullptr, v_target, index, mb,
+                              1.0f / (float)mb, 0.0f, 0.0f, w.h1, w.dz2b, w.dz1, w.xs, w.part_head, w.part_scal, w.mp,
+                              (cudaStream_t)stream);
+        if (rc) return rc;
+        return finish_grads(net, w, (cudaStream_t)stream, w.mp / MP_ALIGN);
+    }
     ppo_fb_kernel<true><<<(unsigned)w.tiles, THREADS, sizeof(FbSmem), (cudaStream_t)stream>>>(
         net->packed, net->params + SAT_PPO_OFF_W2, net->use_tanh, 0.0f, s, nullptr, nullptr, nullptr, v_target, index, mb,
         1.0f / (float)mb, 0.0f, 0.0f, w.h1, w.dz2b, w.dz1, w.xs, w.part_head, w.part_scal, w.mp);
     rc = launch_status();
     if (rc) return rc;
-    return finish_grads(net, w, (cudaStream_t)stream);
+    return finish_grads(net, w, (cudaStream_t)stream, w.tiles);
 }
 
 int sat_ppo_adam(const SatPpoNet* net, const float* lr, float beta1, float beta2, float eps, float max_grad_norm,
