@@ -31,9 +31,13 @@ constexpr int FB_CHUNKS = 1 + 2 * NCH;           // A chunks per tile: x, h1 x 8
 constexpr int FB_SUBS = FB_CHUNKS * NSUB;        // weight sub-chunks per tile: 34
 static_assert(FB_SUBS * B_STAGE == SAT_PPO_TC_IMAGE_BYTES, "header constant out of sync");
 constexpr int XS_LD = 32;
+constexpr int FNSA = 3, FNSB = 3;                // ring depths (the tensor core is not this kernel's limit; the shared memory goes to the staging below)
+constexpr int ST_LD = 20;                        // staging row: 16 floats + 4 of padding (conflict-free 16-byte accesses)
+constexpr int ST_WARP = 32 * ST_LD;              // floats per row warp
 constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + NSA * A_STAGE;
-constexpr int OFF_RED = OFF_B + NSB * B_STAGE;   // head partial sums [NPART][TM] float4
+constexpr int OFF_B = OFF_A + FNSA * A_STAGE;
+constexpr int OFF_STG = OFF_B + FNSB * B_STAGE;  // per-warp transposition staging for the row-major HBM stores / loads
+constexpr int OFF_RED = OFF_STG + 16 * ST_WARP * 4;   // head partial sums [NPART][TM] float4
 constexpr int OFF_DZ3 = OFF_RED + NPART * TM * 16;   // per-row head gradients [TM] float4
 constexpr int OFF_COL = OFF_DZ3 + TM * 16;       // column partial sums [16 warps][4][64]
 constexpr int OFF_SCAL = OFF_COL + 16 * 4 * 64 * 4;  // per-warp scalar partial sums [4][8]
@@ -82,8 +86,62 @@ __device__ __forceinline__ void warp_transpose_sum16(float (&v)[16], int lane) {
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+#ifdef SAT_TC_TRACE
+__device__ unsigned long long g_fb_trace[256];
+__device__ __forceinline__ void fb_trace(int slot) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && slot < 256) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_fb_trace[slot] = t; }
+}
+#define FB_TRACE(slot) fb_trace(slot)
+#else
+#define FB_TRACE(slot)
+#endif
+
+// A row thread holds 64 values of ITS row; written straight to a row-major buffer, every store instruction of a warp would touch
+// 32 rows x 16 bytes (half-used sectors in 32 different lines: 9 us per 128 x 256 tile, measured). These helpers pass 16 values
+// per row at a time through a per-warp staging tile so that each instruction moves whole 32 / 64-byte row segments.
+// v[b * 16 + q * 4 + e] goes to gwarp[row * row_stride + seg_off(b, q) + e]: seg(b, q) = float offset of 16-byte piece q of batch b.
+template <class SegOff>
+__device__ __forceinline__ void store_rows(float* __restrict__ gwarp, int64_t row_stride, const float (&v)[64], float* st, int lane, SegOff seg) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(st + lane * ST_LD + q * 4) = make_float4(v[b * 16 + q * 4], v[b * 16 + q * 4 + 1], v[b * 16 + q * 4 + 2], v[b * 16 + q * 4 + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = i * 32 + lane, rr = idx >> 2, pc = idx & 3;
+            *reinterpret_cast<float4*>(gwarp + rr * row_stride + seg(b, pc)) = *reinterpret_cast<const float4*>(st + rr * ST_LD + pc * 4);
+        }
+        __syncwarp();
+    }
+}
+// v[b * 16 + q * 4 + e] *= act'(g[row][seg(b, q) + e]) with the same access pattern (g = h1)
+template <bool TANH, class SegOff>
+__device__ __forceinline__ void scale_by_act_grad(const float* __restrict__ gwarp, int64_t row_stride, float (&v)[64], float* st, int lane, SegOff seg);
+
 template <bool TANH>
 __device__ __forceinline__ float act_grad_of(float h) { return TANH ? 1.0f - h * h : (h > 0.0f ? 1.0f : 0.0f); }
+
+template <bool TANH, class SegOff>
+__device__ __forceinline__ void scale_by_act_grad(const float* __restrict__ gwarp, int64_t row_stride, float (&v)[64], float* st, int lane, SegOff seg) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = i * 32 + lane, rr = idx >> 2, pc = idx & 3;
+            *reinterpret_cast<float4*>(st + rr * ST_LD + pc * 4) = *reinterpret_cast<const float4*>(gwarp + rr * row_stride + seg(b, pc));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 h = *reinterpret_cast<const float4*>(st + lane * ST_LD + q * 4);
+            v[b * 16 + q * 4] *= act_grad_of<TANH>(h.x); v[b * 16 + q * 4 + 1] *= act_grad_of<TANH>(h.y);
+            v[b * 16 + q * 4 + 2] *= act_grad_of<TANH>(h.z); v[b * 16 + q * 4 + 3] *= act_grad_of<TANH>(h.w);
+        }
+        __syncwarp();
+    }
+}
 
 template <bool CRITIC, bool TANH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -95,6 +153,7 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                  float* __restrict__ part_head, float* __restrict__ part_scal, int64_t mp) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    float* stg = reinterpret_cast<float*>(sm + OFF_STG);
     float4* red = reinterpret_cast<float4*>(sm + OFF_RED);
     float4* dz3s = reinterpret_cast<float4*>(sm + OFF_DZ3);
     float* colp = reinterpret_cast<float*>(sm + OFF_COL);
@@ -103,10 +162,10 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
     float* b1p = reinterpret_cast<float*>(sm + OFF_B1P);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
     uint64_t* b_full = bars;
-    uint64_t* b_empty = bars + NSB;
-    uint64_t* a_full = bars + 2 * NSB;
-    uint64_t* a_empty = a_full + NSA;
-    uint64_t* l1_full = a_empty + NSA;        // layer-1 accumulators complete
+    uint64_t* b_empty = bars + FNSB;
+    uint64_t* a_full = bars + 2 * FNSB;
+    uint64_t* a_empty = a_full + FNSA;
+    uint64_t* l1_full = a_empty + FNSA;        // layer-1 accumulators complete
     uint64_t* l1_read = l1_full + 1;          // ... and read by every row
     uint64_t* l2_full = l1_full + 2;          // layer-2 accumulators complete
     uint64_t* l2_read = l1_full + 3;
@@ -119,8 +178,8 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // >= 1: gridDim.x <= ntiles
 
     if (tid == 0) {
-        for (int i = 0; i < NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < NSA; ++i) { mbar_init(&a_full[i], TC_COMPUTE / 32); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < FNSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < FNSA; ++i) { mbar_init(&a_full[i], TC_COMPUTE / 32); mbar_init(&a_empty[i], 1); }
         mbar_init(l1_full, 1); mbar_init(l1_read, TC_COMPUTE / 32);
         mbar_init(l2_full, 1); mbar_init(l2_read, TC_COMPUTE / 32);
         mbar_init(l3_full, 1); mbar_init(acc_free, TC_COMPUTE / 32);
@@ -175,9 +234,9 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                             if (c == NCH) umma_commit(l2_full);
                             if (c == FB_CHUNKS - 1) umma_commit(l3_full);
                         }
-                        if (++sb == NSB) { sb = 0; bphase ^= 1; }
+                        if (++sb == FNSB) { sb = 0; bphase ^= 1; }
                     }
-                    if (++sa == NSA) { sa = 0; aphase ^= 1; }
+                    if (++sa == FNSA) { sa = 0; aphase ^= 1; }
                 }
             }
         }
@@ -189,10 +248,10 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
             for (int t = 0; t < my_tiles; ++t) {
 #pragma unroll 1
                 for (int idx = 0; idx < FB_SUBS; ++idx, ++pq) {
-                    if (pq >= NSB) mbar_wait(&b_empty[sb], bphase ^ 1);
+                    if (pq >= FNSB) mbar_wait(&b_empty[sb], bphase ^ 1);
                     mbar_expect_tx(&b_full[sb], B_STAGE);
                     bulk_g2s(sm + OFF_B + sb * B_STAGE, image + (size_t)idx * B_STAGE, B_STAGE, &b_full[sb]);
-                    if (++sb == NSB) { sb = 0; bphase ^= 1; }
+                    if (++sb == FNSB) { sb = 0; bphase ^= 1; }
                 }
             }
         }
@@ -209,7 +268,7 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
         auto push_chunk = [&](const float (&v)[UPT]) {
             uint4 H, M, L;
             split8(v, H, M, L);
-            if (qa >= NSA) mbar_wait(&a_empty[sa], aphase ^ 1);
+            if (qa >= FNSA) mbar_wait(&a_empty[sa], aphase ^ 1);
             unsigned char* a0 = sm + OFF_A + sa * A_STAGE + a_off;
             *reinterpret_cast<uint4*>(a0) = H;
             *reinterpret_cast<uint4*>(a0 + A_WORD) = M;
@@ -217,7 +276,7 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             warp_arrive(&a_full[sa]);
             ++qa;
-            if (++sa == NSA) { sa = 0; aphase ^= 1; }
+            if (++sa == FNSA) { sa = 0; aphase ^= 1; }
         };
         // gathers the minibatch rows (ppo_continuous.py:217 s[index]): the layer-1 operand and the padded copy for dW1
         auto produce_x = [&](int tt) {
@@ -241,9 +300,13 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
             const int64_t row = tile_row0(t) + r;
             const bool live = row < n;
+            const int64_t wrow0 = row - lane;                            // first row of this warp's 32 rows
+            float* st = stg + warp * ST_WARP;
             float va[CPT];                                               // pre1 -> h1, then acc2 -> h2 -> dz2, then dh1
             // ---------------- layer 1: h1 = act(W1 x + b1), eight operand chunks, h1 to HBM
+            FB_TRACE(t * 16 + 0);
             mbar_wait(l1_full, t & 1);
+            FB_TRACE(t * 16 + 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             tmem_sum64(lane_base, part * CPT, va);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -260,15 +323,13 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                 }
                 push_chunk(h);
             }
-            // h1 row-major [mp][256]: value kc * 8 + j of this thread is unit 32 kc + 8 part + j
-#pragma unroll
-            for (int kc = 0; kc < NCH; ++kc) {
-                float4* ho = reinterpret_cast<float4*>(h1g + row * HID + kc * KC + part * UPT);
-                ho[0] = make_float4(va[kc * UPT], va[kc * UPT + 1], va[kc * UPT + 2], va[kc * UPT + 3]);
-                ho[1] = make_float4(va[kc * UPT + 4], va[kc * UPT + 5], va[kc * UPT + 6], va[kc * UPT + 7]);
-            }
+            FB_TRACE(t * 16 + 2);
+            // h1 row-major [mp][256]: value kc * 8 + j of this thread is unit 32 kc + 8 part + j (two 32-byte segments per batch)
+            store_rows(h1g + wrow0 * HID, HID, va, st, lane, [&](int b, int pc) { return (2 * b + (pc >> 1)) * KC + part * UPT + (pc & 1) * 4; });
+            FB_TRACE(t * 16 + 3);
             // ---------------- layer 2: h2 = act(W2 h1 + b2) (columns 64 part .. + 63), head pre-activations
             mbar_wait(l2_full, t & 1);
+            FB_TRACE(t * 16 + 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             tmem_sum64(lane_base, part * CPT, va);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -293,6 +354,7 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
 #endif
             }
             asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
+            FB_TRACE(t * 16 + 5);
             // ---------------- per-row loss and its gradient w.r.t. the head pre-activations (quarter 0: one thread per row)
             if (part == 0) {
                 float pre[3];
@@ -354,6 +416,7 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                     for (int k = 0; k < 8; ++k) scal[warp * 8 + k] = rs[k];
             }
             asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
+            FB_TRACE(t * 16 + 6);
             if (tid < 8) part_scal[(int64_t)tile * 8 + tid] = ((scal[tid] + scal[8 + tid]) + scal[16 + tid]) + scal[24 + tid];
             // ---------------- dz2 = (dz3 W3) act'(h2): eight operand chunks of the backward product (K order permuted), the
             // per-tile column sums of dW3 = dz3^T h2 and db2 = sum dz2, dz2 to HBM
@@ -382,13 +445,13 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                         if (!(lane & 1)) cw[(1 + (lane >> 4)) * 64 + kc * UPT + ((lane >> 1) & 7)] = qb_[0];
                     }
                 }
+                FB_TRACE(t * 16 + 7);
                 // dz2 in column blocks [4][mp][64]: this thread's 64 columns are block `part`
-#pragma unroll
-                for (int j4 = 0; j4 < CPT / 4; ++j4)
-                    *reinterpret_cast<float4*>(dz2b + ((int64_t)part * mp + row) * 64 + j4 * 4) =
-                        make_float4(va[j4 * 4], va[j4 * 4 + 1], va[j4 * 4 + 2], va[j4 * 4 + 3]);
+                store_rows(dz2b + ((int64_t)part * mp + wrow0) * 64, 64, va, st, lane, [&](int b, int pc) { return b * 16 + pc * 4; });
             }
-            if (t + 1 < my_tiles) produce_x(t + 1);                      // into the ring behind this tile's last chunk
+            FB_TRACE(t * 16 + 8);
+            if (t + 1 < my_tiles) produce_x(t + 1);
+            FB_TRACE(t * 16 + 9);                      // into the ring behind this tile's last chunk
             asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
             {
                 // the four row groups of every quarter, in a fixed order: rows 0..heads-1 = dW3, row 3 = db2
@@ -402,20 +465,21 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                 }
             }
             // ---------------- dz1 = (dz2 W2) act'(h1) -> HBM row-major (columns 64 part .. + 63 = input units)
+            FB_TRACE(t * 16 + 10);
             mbar_wait(l3_full, t & 1);
+            FB_TRACE(t * 16 + 11);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             tmem_sum64(lane_base, part * CPT, va);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             warp_arrive(acc_free);
 #ifndef SAT_FB_DEBUG_H2
-#pragma unroll
-            for (int j4 = 0; j4 < CPT / 4; ++j4) {
-                const int64_t o = row * HID + part * CPT + j4 * 4;
-                const float4 hv = *reinterpret_cast<const float4*>(h1g + o);
-                *reinterpret_cast<float4*>(dz1g + o) = make_float4(va[j4 * 4] * act_grad_of<TANH>(hv.x), va[j4 * 4 + 1] * act_grad_of<TANH>(hv.y),
-                                                                  va[j4 * 4 + 2] * act_grad_of<TANH>(hv.z), va[j4 * 4 + 3] * act_grad_of<TANH>(hv.w));
+            {
+                auto seg = [&](int b, int pc) { return part * CPT + b * 16 + pc * 4; };
+                scale_by_act_grad<TANH>(h1g + wrow0 * HID, HID, va, st, lane, seg);
+                store_rows(dz1g + wrow0 * HID, HID, va, st, lane, seg);
             }
 #endif
+            FB_TRACE(t * 16 + 12);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -432,6 +496,10 @@ int set_smem(K kernel) {
 }
 
 }  // namespace
+
+#ifdef SAT_TC_TRACE
+extern "C" int sat_debug_fb_tc_trace(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_fb_trace, sizeof(g_fb_trace)); }
+#endif
 
 int ppo_fb_tc_launch(bool critic, bool use_tanh, const float* packed, unsigned char* image, float max_action, const float* s,
                      const float* a, const float* old_logp, const float* adv, const float* v_target, const int64_t* index,
