@@ -32,6 +32,7 @@ UNITS = {
     "actor_tc.cu": [],
     "ppo_update.cu": [],
     "ppo_fb_tc.cu": [],
+    "ppo_wgrad2_tc.cu": [],
     "capi.cu": [],
 }
 

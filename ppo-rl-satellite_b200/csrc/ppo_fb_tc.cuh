@@ -11,3 +11,6 @@ int ppo_fb_tc_launch(bool critic, bool use_tanh, const float* packed, unsigned c
                      const float* a, const float* old_logp, const float* adv, const float* v_target, const int64_t* index,
                      int64_t n, float inv_n, float epsilon, float entropy_coef, float* h1g, float* dz2b, float* dz1g, float* xs,
                      float* part_head, float* part_scal, int64_t mp, cudaStream_t stream);
+
+// dW2 = dz2^T h1 on the tensor cores (ppo_wgrad2_tc.cu): same operands / output as ppo_wgrad2_kernel; part_w2 [slabs][256][256]
+int ppo_wgrad2_tc_launch(const float* dz2b, const float* h1g, int64_t mp, int slabs, float* part_w2, cudaStream_t stream);

@@ -641,14 +641,22 @@ int check_net(const SatPpoNet* net) {
 }
 
 // everything after the forward/backward kernel: weight-gradient kernels and the partial sums
-int finish_grads(const SatPpoNet* net, const Workspace& w, cudaStream_t stream, int64_t head_tiles) {
+int finish_grads(const SatPpoNet* net, const Workspace& w, cudaStream_t stream, int64_t head_tiles, bool tc) {
     const int heads = net->heads;
     const int64_t ktiles = w.mp / KT;
-    const int slabs2 = (int)(ktiles < W2_SLABS ? ktiles : W2_SLABS);
     const int slabs1 = (int)(w.mp / 16 < W1_SLABS ? w.mp / 16 : W1_SLABS);
-    int rc = set_smem(ppo_wgrad2_kernel, sizeof(WgSmem));
-    if (rc) return rc;
-    ppo_wgrad2_kernel<<<dim3(4, slabs2), THREADS, sizeof(WgSmem), stream>>>(w.dz2b, w.h1, w.mp, slabs2, w.part_w2);
+    int rc;
+    int slabs2 = (int)(ktiles < W2_SLABS ? ktiles : W2_SLABS);
+    if (tc) {
+        const int64_t chunks = w.mp / 32;
+        slabs2 = (int)(chunks < W2_SLABS ? chunks : W2_SLABS);
+        rc = ppo_wgrad2_tc_launch(w.dz2b, w.h1, w.mp, slabs2, w.part_w2, stream);
+        if (rc) return rc;
+    } else {
+        rc = set_smem(ppo_wgrad2_kernel, sizeof(WgSmem));
+        if (rc) return rc;
+        ppo_wgrad2_kernel<<<dim3(4, slabs2), THREADS, sizeof(WgSmem), stream>>>(w.dz2b, w.h1, w.mp, slabs2, w.part_w2);
+    }
     rc = set_smem(ppo_wgrad1_kernel, sizeof(W1Smem));
     if (rc) return rc;
     ppo_wgrad1_kernel<<<slabs1, HID, sizeof(W1Smem), stream>>>(w.dz1, w.xs, w.mp, slabs1, w.part_w1, w.part_b1);
@@ -711,14 +719,14 @@ int sat_ppo_actor_grad(const SatPpoNet* net, const float* s, const float* a, con
                               1.0f / (float)mb, epsilon, entropy_coef, w.h1, w.dz2b, w.dz1, w.xs, w.part_head, w.part_scal, w.mp,
                               (cudaStream_t)stream);
         if (rc) return rc;
-        return finish_grads(net, w, (cudaStream_t)stream, w.mp / MP_ALIGN);
+        return finish_grads(net, w, (cudaStream_t)stream, w.mp / MP_ALIGN, true);
     }
     ppo_fb_kernel<false><<<(unsigned)w.tiles, THREADS, sizeof(FbSmem), (cudaStream_t)stream>>>(
         net->packed, net->params + SAT_PPO_OFF_W2, net->use_tanh, net->max_action, s, a, old_logp, adv, nullptr, index, mb,
         1.0f / (float)mb, epsilon, entropy_coef, w.h1, w.dz2b, w.dz1, w.xs, w.part_head, w.part_scal, w.mp);
     rc = launch_status();
     if (rc) return rc;
-    return finish_grads(net, w, (cudaStream_t)stream, w.tiles);
+    return finish_grads(net, w, (cudaStream_t)stream, w.tiles, false);
 }
 
 int sat_ppo_critic_grad(const SatPpoNet* net, const float* s, const float* v_target, const int64_t* index, int64_t mb,
@@ -735,14 +743,14 @@ int sat_ppo_critic_grad(const SatPpoNet* net, const float* s, const float* v_tar
                               1.0f / (float)mb, 0.0f, 0.0f, w.h1, w.dz2b, w.dz1, w.xs, w.part_head, w.part_scal, w.mp,
                               (cudaStream_t)stream);
         if (rc) return rc;
-        return finish_grads(net, w, (cudaStream_t)stream, w.mp / MP_ALIGN);
+        return finish_grads(net, w, (cudaStream_t)stream, w.mp / MP_ALIGN, true);
     }
     ppo_fb_kernel<true><<<(unsigned)w.tiles, THREADS, sizeof(FbSmem), (cudaStream_t)stream>>>(
         net->packed, net->params + SAT_PPO_OFF_W2, net->use_tanh, 0.0f, s, nullptr, nullptr, nullptr, v_target, index, mb,
         1.0f / (float)mb, 0.0f, 0.0f, w.h1, w.dz2b, w.dz1, w.xs, w.part_head, w.part_scal, w.mp);
     rc = launch_status();
     if (rc) return rc;
-    return finish_grads(net, w, (cudaStream_t)stream, w.tiles);
+    return finish_grads(net, w, (cudaStream_t)stream, w.tiles, false);
 }
 
 int sat_ppo_adam(const SatPpoNet* net, const float* lr, float beta1, float beta2, float eps, float max_grad_norm,
