@@ -88,3 +88,26 @@ def test_tc_ragged_sizes_and_env_state_path(eng):
     assert torch.equal(o0, o1)
     torch.testing.assert_close(a1, a0, rtol=0, atol=1e-5)
     torch.testing.assert_close(l1, l0, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.timeout(180)
+def test_observe_norm_is_the_fused_paths_arithmetic(eng):
+    """sat_env_observe_norm (the fp32 observation the tensor-core actor path reads): (x - mean) / (std + 1e-8) in fp64, then the
+    cast - environment.py:76-77 + normalization.py:41 - bit for bit, with and without statistics, ragged sizes"""
+    import ctypes as C
+    from ppo_rl_satellite_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(3)
+    for n in (1, 127, 128, 1000):
+        env = eng.EnvBatch(n, mode="cw", d_capture=20000.0, max_episode_steps=10)
+        env.set_state(np.array([200000.0, 0, 0]) + rng.normal(0, 3e4, (n, 3)), rng.normal(0, 3.0, (n, 3)),
+                      np.array([18000.0, 0, 0]) + rng.normal(0, 3e4, (n, 3)), rng.normal(0, 3.0, (n, 3)))
+        st = eng.RunningStats(18)
+        x = env.observe()                                       # fp64 [n, 18]
+        st.update_normalize(x)
+        out = torch.empty((n, 18), dtype=torch.float32, device="cuda")
+        L.check(lib.sat_env_observe_norm(C.byref(env.st), L.ptr(st.buf), L.ptr(out), L.stream_ptr()), "observe_norm")
+        ref = ((x - st.mean) / (st.std + 1e-8)).float()
+        assert torch.equal(out, ref)
+        L.check(lib.sat_env_observe_norm(C.byref(env.st), None, L.ptr(out), L.stream_ptr()), "observe_norm")
+        assert torch.equal(out, x.float())

@@ -48,8 +48,19 @@ def _flat_grads(module, names):
     return torch.cat([named[k].grad.reshape(-1) for k in names])
 
 
-@pytest.mark.parametrize("use_tanh,mb", [(1, 1000), (0, 1000), (1, 64), (1, 37)])
-def test_fused_gradients_match_autograd(use_tanh, mb):
+@pytest.fixture(params=[1, 0], ids=["tensor-cores", "ffma2"])
+def fb_path(request):
+    """both forward/backward implementations of the fused step: csrc/ppo_fb_tc.cu + ppo_wgrad2_tc.cu (default) and the fp32
+    FFMA2 kernels of csrc/ppo_update.cu"""
+    from ppo_rl_satellite_b200 import _lib as L
+    lib = L.load()
+    prev = lib.sat_ppo_use_tensor_cores(request.param)
+    yield request.param
+    lib.sat_ppo_use_tensor_cores(prev)
+
+
+@pytest.mark.parametrize("use_tanh,mb", [(1, 1000), (0, 1000), (1, 64), (1, 37), (1, 300)])
+def test_fused_gradients_match_autograd(use_tanh, mb, fb_path):
     from ppo_rl_satellite_b200 import engine as E
     args = _args(use_tanh=use_tanh)
     fused, eager = _pair(args)
