@@ -101,20 +101,22 @@ __device__ __forceinline__ void fb_trace(int slot) {
 // per row at a time through a per-warp staging tile so that each instruction moves whole 32 / 64-byte row segments.
 // v[b * 16 + q * 4 + e] goes to gwarp[row * row_stride + seg_off(b, q) + e]: seg(b, q) = float offset of 16-byte piece q of batch b.
 template <class SegOff>
+__device__ __forceinline__ void store_rows_batch(int b, float* __restrict__ gwarp, int64_t row_stride, const float (&v)[64], float* st, int lane, SegOff seg) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(st + lane * ST_LD + q * 4) = make_float4(v[b * 16 + q * 4], v[b * 16 + q * 4 + 1], v[b * 16 + q * 4 + 2], v[b * 16 + q * 4 + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = i * 32 + lane, rr = idx >> 2, pc = idx & 3;
+        *reinterpret_cast<float4*>(gwarp + rr * row_stride + seg(b, pc)) = *reinterpret_cast<const float4*>(st + rr * ST_LD + pc * 4);
+    }
+    __syncwarp();
+}
+template <class SegOff>
 __device__ __forceinline__ void store_rows(float* __restrict__ gwarp, int64_t row_stride, const float (&v)[64], float* st, int lane, SegOff seg) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(st + lane * ST_LD + q * 4) = make_float4(v[b * 16 + q * 4], v[b * 16 + q * 4 + 1], v[b * 16 + q * 4 + 2], v[b * 16 + q * 4 + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = i * 32 + lane, rr = idx >> 2, pc = idx & 3;
-            *reinterpret_cast<float4*>(gwarp + rr * row_stride + seg(b, pc)) = *reinterpret_cast<const float4*>(st + rr * ST_LD + pc * 4);
-        }
-        __syncwarp();
-    }
+    for (int b = 0; b < 4; ++b) store_rows_batch(b, gwarp, row_stride, v, st, lane, seg);
 }
 // v[b * 16 + q * 4 + e] *= act'(g[row][seg(b, q) + e]) with the same access pattern (g = h1)
 template <bool TANH, class SegOff>
@@ -322,10 +324,12 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                     va[kc * UPT + j] = hh.x; va[kc * UPT + j + 1] = hh.y;
                 }
                 push_chunk(h);
+                // h1 row-major [mp][256] (value kc * 8 + j of this thread is unit 32 kc + 8 part + j): two chunks = one batch of
+                // two 32-byte segments per row, stored while the ring waits for the tensor core
+                if (kc & 1)
+                    store_rows_batch(kc >> 1, h1g + wrow0 * HID, HID, va, st, lane, [&](int b, int pc) { return (2 * b + (pc >> 1)) * KC + part * UPT + (pc & 1) * 4; });
             }
             FB_TRACE(t * 16 + 2);
-            // h1 row-major [mp][256]: value kc * 8 + j of this thread is unit 32 kc + 8 part + j (two 32-byte segments per batch)
-            store_rows(h1g + wrow0 * HID, HID, va, st, lane, [&](int b, int pc) { return (2 * b + (pc >> 1)) * KC + part * UPT + (pc & 1) * 4; });
             FB_TRACE(t * 16 + 3);
             // ---------------- layer 2: h2 = act(W2 h1 + b2) (columns 64 part .. + 63), head pre-activations
             mbar_wait(l2_full, t & 1);
@@ -444,10 +448,11 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                         warp_transpose_sum16(qb_, lane);
                         if (!(lane & 1)) cw[(1 + (lane >> 4)) * 64 + kc * UPT + ((lane >> 1) & 7)] = qb_[0];
                     }
+                    // dz2 in column blocks [4][mp][64]: this thread's 64 columns are block `part`
+                    if (kc & 1)
+                        store_rows_batch(kc >> 1, dz2b + ((int64_t)part * mp + wrow0) * 64, 64, va, st, lane, [&](int b, int pc) { return b * 16 + pc * 4; });
                 }
                 FB_TRACE(t * 16 + 7);
-                // dz2 in column blocks [4][mp][64]: this thread's 64 columns are block `part`
-                store_rows(dz2b + ((int64_t)part * mp + wrow0) * 64, 64, va, st, lane, [&](int b, int pc) { return b * 16 + pc * 4; });
             }
             FB_TRACE(t * 16 + 8);
             if (t + 1 < my_tiles) produce_x(t + 1);
