@@ -351,7 +351,11 @@ def run_ppo_section(args, rank, world, dev, torch, dist, eng):
     return {"ppo_samples_per_sec": samples / (tc + tu), "rollout_s": tc, "update_s": tu, "samples": samples,
             "config": f"T={T} x {n} envs/GPU (rk4 mode, S={args.substeps}), minibatch {mb}/GPU, K=10, gamma .99, lambda .95 "
                       f"(CPPO_main.py:24-27); config 5 proper is --ppo-horizon 2048 --ppo-envs 8192 on 8 GPUs",
-            "optimizer_steps": 10 * -(-T * n // mb), "update_impl": "fused CUDA kernels (csrc/ppo_update.cu), actor and critic chains on two streams" if fused else "PyTorch autograd + torch.optim.Adam",
+            "optimizer_steps": 10 * -(-T * n // mb), "update_impl": ("fused CUDA kernels, actor and critic chains on two streams: forward/backward (csrc/ppo_fb_tc.cu) and dW2 "
+                                                                 "(csrc/ppo_wgrad2_tc.cu) on the tensor cores as exact bf16x3 splits, dW1 / partial sums / Adam fp32 (csrc/ppo_update.cu)"
+                                                                 if eng.L.load().sat_ppo_use_tensor_cores(-1) else
+                                                                 "fused CUDA kernels, fp32 FFMA2 (csrc/ppo_update.cu; SAT_PPO_TC=0), actor and critic chains on two streams")
+                                                                if fused else "PyTorch autograd + torch.optim.Adam",
             "cuda_graph": bool(not fused and use_graph and agent._graph is not None), "allreduce": None if world == 1 else (
                 "fused into the Adam kernel: every rank reads all ranks' flat gradients (286 KB + 284 KB) from NVLink peer memory "
                 "(torch symmetric memory) in rank order after a device-side barrier; no NCCL call on the step"
@@ -662,6 +666,9 @@ def run_ours(args, rank, world, local_rank):
         per_gpu_sample_steps = ppo["samples"] / world * 10
         ppo["optimizer_step_ms"] = 1e3 * ppo["update_s"] / ppo["optimizer_steps"]
         ppo["update_fp32_tflops_per_gpu"] = FLOP_PPO_SAMPLE_STEP * per_gpu_sample_steps / ppo["update_s"] / 1e12
+        ppo["update_fp32_tflops_per_gpu_what"] = ("useful fp32 FLOPs of the update (827 392 per sample-step) per second; on the tensor-core path the "
+                                                  "two 256-wide layer products and dW2 issue 6 bf16 word products per fp32 product, so this can exceed "
+                                                  "the CUDA-core FFMA rate")
         ppo["update_frac_of_nominal_fp32_peak"] = ppo["update_fp32_tflops_per_gpu"] / FP32_NOMINAL_TFLOPS
         ppo["update_frac_of_measured_ffma_chain"] = ppo["update_fp32_tflops_per_gpu"] / peak32
         ppo["update_flops_per_sample_step"] = FLOP_PPO_SAMPLE_STEP
