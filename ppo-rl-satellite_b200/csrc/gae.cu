@@ -33,14 +33,18 @@ __device__ __forceinline__ float gae_step(float delta, float gl, float gae, floa
 // the scan of tile i, so the kernel is limited by HBM (17 B/sample), not by the length of one env's dependency chain -
 // the one-thread-per-env form reached 7 % of HBM at the config-5 shard (T = 2048, N = 8192: 64 CTAs, 2048 dependent steps).
 constexpr int kGaeTile = 64;      // time steps per tile
-constexpr int kGaeEnvs = 32;      // envs per CTA
+// envs per CTA (template parameter): 32 (a 128-byte row segment) when there are enough envs to fill the GPU with such CTAs; at
+// the config-5 shard (N = 8192) that gives only 256 CTAs = 1.7 per SM, each a serial chain of 32 tiles, and the kernel sat at
+// 0.37 of HBM, so narrower CTAs (16 or 8 envs: 64- / 32-byte segments, still whole sectors) are used to put more independent
+// scans on every SM.
 constexpr int kGaeThreads = 256;
-constexpr int kGaePer = kGaeTile * kGaeEnvs / kGaeThreads;   // elements per thread per tile
 
+template <int kGaeEnvs>
 __global__ void __launch_bounds__(kGaeThreads)
 gae_time_major_kernel(const float* __restrict__ r, const float* __restrict__ v, const uint8_t* __restrict__ done,
                       const float* __restrict__ r_scale, int64_t T, int64_t N, float gamma, float gl,
                       float* __restrict__ adv, float* __restrict__ vt) {
+    constexpr int kGaePer = kGaeTile * kGaeEnvs / kGaeThreads;   // elements per thread per tile
     __shared__ float s_x[kGaeTile][kGaeEnvs];      // reward, then delta, then gae
     __shared__ float s_v[kGaeTile][kGaeEnvs];      // vs
     __shared__ float s_d[kGaeTile][kGaeEnvs];      // done as 0 / 1
@@ -253,8 +257,10 @@ int sat_gae(const float* r, const float* v, const uint8_t* done, const float* r_
     if (!r || !v || !done || !adv || !v_target) return SAT_ERR_NULL;
     if (T <= 0 || N <= 0) return SAT_ERR_SIZE;
     const float gl = (float)((double)gamma * (double)lamda);   // python float product, weak-cast to fp32
-    const unsigned blocks = (unsigned)((N + kGaeEnvs - 1) / kGaeEnvs);
-    gae_time_major_kernel<<<blocks, kGaeThreads, 0, (cudaStream_t)stream>>>(r, v, done, r_scale, T, N, gamma, gl, adv, v_target);
+    // at least ~6 CTAs per SM (148 SMs) where the env count allows it
+    if (N >= 32 * 888) gae_time_major_kernel<32><<<(unsigned)((N + 31) / 32), kGaeThreads, 0, (cudaStream_t)stream>>>(r, v, done, r_scale, T, N, gamma, gl, adv, v_target);
+    else if (N >= 16 * 296) gae_time_major_kernel<16><<<(unsigned)((N + 15) / 16), kGaeThreads, 0, (cudaStream_t)stream>>>(r, v, done, r_scale, T, N, gamma, gl, adv, v_target);
+    else gae_time_major_kernel<8><<<(unsigned)((N + 7) / 8), kGaeThreads, 0, (cudaStream_t)stream>>>(r, v, done, r_scale, T, N, gamma, gl, adv, v_target);
     return launch_status();
 }
 
