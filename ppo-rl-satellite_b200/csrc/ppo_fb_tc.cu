@@ -511,11 +511,16 @@ int ppo_fb_tc_launch(bool critic, bool use_tanh, const float* packed, unsigned c
                      int64_t n, float inv_n, float epsilon, float entropy_coef, float* h1g, float* dz2b, float* dz1g, float* xs,
                      float* part_head, float* part_scal, int64_t mp, cudaStream_t stream) {
     if (mp % TM) return SAT_ERR_SIZE;
-    int dev = 0, sms = 0;
+    static int sm_count[64] = {0};
+    int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return (int)e;
+    int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 0;
+    if (sms <= 0) {
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) sm_count[dev] = sms;
+    }
     // the image is rebuilt from the packed weights on every call: the Adam kernel rewrites them after every minibatch
     ppo_fb_tc_pack_kernel<<<(FB_CHUNKS * 4 * HID + 255) / 256, 256, 0, stream>>>(packed, image);
     const int64_t tiles = mp / TM;

@@ -1,6 +1,6 @@
-"""K3 on the tensor cores (csrc/actor_tc.cu): the 3xTF32 tcgen05 path of the actor's hidden layer against an fp64 ground
+"""K3 on the tensor cores (csrc/actor_tc.cu): the exact-bf16x3 tcgen05 path of the actor's dense layers against an fp64 ground
 truth, next to the fp32 FFMA2 path (csrc/actor.cu). The reference evaluates Actor_Gaussian in fp32
-(ppo_continuous.py:83-95); the tensor-core path is admissible only if it is as close to the exact result as fp32 FMA is."""
+(ppo_continuous.py:83-95); the tensor-core path is the default because it is as close to the exact result as fp32 FMA is."""
 import numpy as np
 import pytest
 
@@ -54,13 +54,12 @@ def test_tc_hidden_layer_is_as_accurate_as_fp32_fma(eng, use_tanh):
     err_fma = np.abs(out[False][0] - truth)
     err_tc = np.abs(out[True][0] - truth)
     print(f"use_tanh={use_tanh}: |mean - fp64| FFMA2 max {err_fma.max():.2e} rms {np.sqrt((err_fma**2).mean()):.2e}; "
-          f"3xTF32 max {err_tc.max():.2e} rms {np.sqrt((err_tc**2).mean()):.2e}")
-    assert err_tc.max() < 2e-6                                           # fp32-level (plain TF32 would be ~1e-3)
-    # tanh networks (the reference's default, CPPO_main.py:37): no worse than the FFMA2 path within 1.5x; ReLU lets the
-    # truncating tensor-core accumulation show more (activations are not squashed): within 2.5x
-    bar = 1.5 if use_tanh else 2.5
-    assert np.sqrt((err_tc ** 2).mean()) <= bar * np.sqrt((err_fma ** 2).mean()) + 1e-8
-    assert err_tc.max() <= 2.5 * err_fma.max() + 1e-7
+          f"tensor cores max {err_tc.max():.2e} rms {np.sqrt((err_tc**2).mean()):.2e}")
+    assert err_tc.max() < 2e-6                                           # fp32-level (plain bf16 / TF32 would be ~1e-3)
+    # the bar that makes the tensor-core path the default: its rms error against the fp64 truth is no larger than the fp32
+    # FFMA2 kernel's (measured 6.5e-8 vs 7.2e-8 with tanh, 3.3e-8 vs 3.5e-8 with ReLU); single worst elements within 1.25x
+    assert np.sqrt((err_tc ** 2).mean()) <= np.sqrt((err_fma ** 2).mean())
+    assert err_tc.max() <= 1.25 * err_fma.max() + 2e-8
     np.testing.assert_allclose(out[True][1], out[False][1], rtol=0, atol=1e-5)
     np.testing.assert_allclose(out[True][2], out[False][2], rtol=1e-4, atol=1e-4)
 
