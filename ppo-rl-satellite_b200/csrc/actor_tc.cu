@@ -62,6 +62,9 @@ static_assert(NCHUNK * NSUB * B_STAGE <= SAT_ACTOR_TC_IMAGE_FLOATS * 4, "weight 
 // W2T[k][n] = fc2.weight[n][k]). One thread = 8 consecutive k of one n (coalesced over n).
 __global__ void actor_tc_pack_kernel(const float* __restrict__ packed0, unsigned char* __restrict__ image0,
                                      const float* __restrict__ packed1, unsigned char* __restrict__ image1) {
+    // programmatic dependent launch: the sampling kernel may start its prologue (barriers, TMEM, tables, first observation
+    // operand) now; its weight-stream lane waits for this grid to complete before it reads the image
+    asm volatile("griddepcontrol.launch_dependents;");
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= NCHUNK * 4 * HID) return;
     const float* __restrict__ packed = blockIdx.y ? packed1 : packed0;
@@ -291,6 +294,7 @@ actor_tc_kernel(const __grid_constant__ TcNet net0, const __grid_constant__ TcNe
         // ------------------------------------------------------------------ weight stream: 24 KB sub-chunks, W1 then W2, tile after tile
         if (tid == TC_COMPUTE + 32) {
             constexpr int SUBS = NCHUNK * NSUB;                          // weight sub-chunks per tile: 18
+            asm volatile("griddepcontrol.wait;" ::: "memory");           // the image's pack kernel (launched just before) is complete
             int sb = 0, bphase = 0, pq = 0;
 #pragma unroll 1
             for (int t = 0; t < my_tiles; ++t) {
@@ -512,11 +516,15 @@ int launch_tc(const SatActorWeights* wa, float* image_a, const SatActorWeights* 
     if (!obs_f32) s0 = *st;
     const int64_t work = ((n + TM - 1) / TM) * nnet;
     const unsigned blocks = (unsigned)(work < sms ? work : sms);          // persistent: one CTA per SM walks over the tiles
-    if (wa->use_tanh)
-        actor_tc_kernel<true><<<blocks, TC_THREADS, TC_SMEM, s>>>(n0, n1, nnet, obs_f32, s0, obs_stats, n, row_offset, seed, obs_out);
-    else
-        actor_tc_kernel<false><<<blocks, TC_THREADS, TC_SMEM, s>>>(n0, n1, nnet, obs_f32, s0, obs_stats, n, row_offset, seed, obs_out);
-    return launch_status();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // overlap this kernel's prologue with the pack kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = wa->use_tanh ? cudaLaunchKernelEx(&cfg, actor_tc_kernel<true>, n0, n1, nnet, obs_f32, s0, obs_stats, n, row_offset, seed, obs_out)
+                     : cudaLaunchKernelEx(&cfg, actor_tc_kernel<false>, n0, n1, nnet, obs_f32, s0, obs_stats, n, row_offset, seed, obs_out);
+    return e == cudaSuccess ? launch_status() : (int)e;
 }
 }  // namespace
 

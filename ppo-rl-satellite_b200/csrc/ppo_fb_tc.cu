@@ -51,6 +51,7 @@ static_assert(FB_SMEM <= 227 * 1024, "shared memory budget");
 // image: chunk 0 = W1 (as in actor_tc.cu), chunks 1..8 = W2 forward (n = output unit j, k = input unit), chunks 9..16 = W2
 // backward (n = input unit i, k = output unit j in the permuted order: position kk = 8 p + jj of chunk kc is j = 64 p + 8 kc + jj)
 __global__ void ppo_fb_tc_pack_kernel(const float* __restrict__ packed, unsigned char* __restrict__ image) {
+    asm volatile("griddepcontrol.launch_dependents;");                  // see actor_tc_pack_kernel
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= FB_CHUNKS * 4 * HID) return;
     const int n = idx % HID, c16 = (idx / HID) & 3, chunk = idx / (4 * HID);
@@ -245,6 +246,7 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
     } else if (warp == TC_COMPUTE / 32 + 1) {
         // ------------------------------------------------------------------ weight stream
         if (tid == TC_COMPUTE + 32) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");           // the image's pack kernel (launched just before) is complete
             int sb = 0, bphase = 0, pq = 0;
 #pragma unroll 1
             for (int t = 0; t < my_tiles; ++t) {
@@ -525,13 +527,19 @@ int ppo_fb_tc_launch(bool critic, bool use_tanh, const float* packed, unsigned c
     ppo_fb_tc_pack_kernel<<<(FB_CHUNKS * 4 * HID + 255) / 256, 256, 0, stream>>>(packed, image);
     const int64_t tiles = mp / TM;
     const unsigned blocks = (unsigned)(tiles < sms ? tiles : sms);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = FB_SMEM; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // overlap the kernel's prologue with the pack kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
 #define SAT_FB_LAUNCH(C, T)                                                                                                    \
     do {                                                                                                                       \
         int rc = set_smem(ppo_fb_tc_kernel<C, T>);                                                                            \
         if (rc) return rc;                                                                                                     \
-        ppo_fb_tc_kernel<C, T><<<blocks, TC_THREADS, FB_SMEM, stream>>>(packed, image, max_action, s, a, old_logp, adv, v_target, index, \
-                                                                        n, inv_n, epsilon, entropy_coef, h1g, dz2b, dz1g, xs,    \
-                                                                        part_head, part_scal, mp);                              \
+        e = cudaLaunchKernelEx(&cfg, ppo_fb_tc_kernel<C, T>, packed, (const unsigned char*)image, max_action, s, a, old_logp, adv, v_target,    \
+                               index, n, inv_n, epsilon, entropy_coef, h1g, dz2b, dz1g, xs, part_head, part_scal, mp);          \
+        if (e != cudaSuccess) return (int)e;                                                                                   \
     } while (0)
     if (critic) { if (use_tanh) SAT_FB_LAUNCH(true, true); else SAT_FB_LAUNCH(true, false); }
     else { if (use_tanh) SAT_FB_LAUNCH(false, true); else SAT_FB_LAUNCH(false, false); }
