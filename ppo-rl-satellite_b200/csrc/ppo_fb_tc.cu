@@ -283,10 +283,11 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
             if (++sa == FNSA) { sa = 0; aphase ^= 1; }
         };
         // gathers the minibatch rows (ppo_continuous.py:217 s[index]): the layer-1 operand and the padded copy for dW1
-        auto produce_x = [&](int tt) {
+        // source row of minibatch row `row` (ppo_continuous.py:217 index), fetched a phase ahead of its uses
+        auto src_of = [&](int64_t row) { return row < n ? (index ? index[row] : row) : (int64_t)0; };
+        auto produce_x = [&](int tt, int64_t src) {
             const int64_t row = tile_row0(tt) + r;
             const bool live = row < n;
-            const int64_t src = live ? (index ? index[row] : row) : 0;
             const int k0 = part * UPT;
             float v[UPT], xv[UPT];
 #pragma unroll
@@ -298,13 +299,15 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
             xo[0] = make_float4(xv[0], xv[1], xv[2], xv[3]);
             xo[1] = make_float4(xv[4], xv[5], xv[6], xv[7]);
         };
-        produce_x(0);
+        produce_x(0, src_of(tile_row0(0) + r));
 #pragma unroll 1
         for (int t = 0; t < my_tiles; ++t) {
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
             const int64_t row = tile_row0(t) + r;
             const bool live = row < n;
             const int64_t wrow0 = row - lane;                            // first row of this warp's 32 rows
+            const int64_t src = src_of(row);                             // used by the loss phase
+            const int64_t src_next = (t + 1 < my_tiles) ? src_of(tile_row0(t + 1) + r) : 0;
             float* st = stg + warp * ST_WARP;
             float va[CPT];                                               // pre1 -> h1, then acc2 -> h2 -> dz2, then dh1
             // ---------------- layer 1: h1 = act(W1 x + b1), eight operand chunks, h1 to HBM
@@ -340,6 +343,16 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
             tmem_sum64(lane_base, part * CPT, va);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             warp_arrive(l2_read);
+            // the loss phase's per-row inputs (quarter 0 only), in flight during the head sums
+            float la[3] = {0.0f, 0.0f, 0.0f}, lo[3] = {0.0f, 0.0f, 0.0f}, ladv = 0.0f;
+            if (part == 0 && live) {
+                if (CRITIC) ladv = v_target[src];
+                else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { la[k] = a[src * 3 + k]; lo[k] = old_logp[src * 3 + k]; }
+                    ladv = adv[src];
+                }
+            }
             {
                 float2 p0 = make_float2(0.0f, 0.0f), p1 = p0, p2 = p0;
 #pragma unroll
@@ -374,10 +387,9 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
 #endif
                 float d3[3] = {0.0f, 0.0f, 0.0f}, dls[3] = {0.0f, 0.0f, 0.0f}, loss = 0.0f;
                 if (live) {
-                    const int64_t src = index ? index[row] : row;
                     if (CRITIC) {
                         const float v = pre[0] + __ldg(packed + OFF_B3);
-                        const float diff = v - v_target[src];
+                        const float diff = v - ladv;
                         loss = diff * diff * inv_n;                                                    // :233
                         d3[0] = 2.0f * diff * inv_n;
                     } else {
@@ -388,13 +400,13 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                             mean[k] = max_action * th[k];
                             const float ls = __ldg(packed + OFF_LS + k);
                             sd[k] = expf(ls);
-                            x[k] = a[src * 3 + k];
+                            x[k] = la[k];
                             const float diff = x[k] - mean[k];
-                            lsum += -(diff * diff) / (2.0f * sd[k] * sd[k]) - ls - 0.9189385332046727f - old_logp[src * 3 + k];   // :219-221
+                            lsum += -(diff * diff) / (2.0f * sd[k] * sd[k]) - ls - 0.9189385332046727f - lo[k];   // :219-221
                             ent += 1.4189385332046727f + ls;                                           // :218 Normal.entropy()
                         }
                         const float ratio = expf(lsum);
-                        const float A = adv[src];
+                        const float A = ladv;
                         const float surr1 = ratio * A;
                         const bool inside = ratio >= 1.0f - epsilon && ratio <= 1.0f + epsilon;
                         const float surr2 = fminf(fmaxf(ratio, 1.0f - epsilon), 1.0f + epsilon) * A;   // :224
@@ -457,7 +469,7 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                 FB_TRACE(t * 16 + 7);
             }
             FB_TRACE(t * 16 + 8);
-            if (t + 1 < my_tiles) produce_x(t + 1);
+            if (t + 1 < my_tiles) produce_x(t + 1, src_next);
             FB_TRACE(t * 16 + 9);                      // into the ring behind this tile's last chunk
             asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
             {
