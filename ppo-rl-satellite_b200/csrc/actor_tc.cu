@@ -128,31 +128,18 @@ __device__ __forceinline__ void produce_x(unsigned char* xs, uint32_t a_off, int
             for (int j = 0; j < 4; ++j) {
                 const int k = k0 + h + j;
                 double y = (k < 6) ? ya[j] - yb[j] : ya[j];
-#ifdef SAT_TC_NODIV
-                if (obs_stats) y = (y - mu[j]) * (sd[j] + 1e-8);
-#else
                 if (obs_stats) y = (y - mu[j]) / (sd[j] + 1e-8);
-#endif
                 xv[h + j] = (k < IN) ? (float)y : 0.0f;
             }
         }
     }
-#ifdef SAT_TC_TRACE
-    if (threadIdx.x == 0 && xv[0] != 12345.678f) TC_TRACE(1, 200);
-#endif
     uint4 H, M, L;
     split8(xv, H, M, L);
     unsigned char* a0 = xs + a_off;
     *reinterpret_cast<uint4*>(a0) = H;
     *reinterpret_cast<uint4*>(a0 + A_WORD) = M;
     *reinterpret_cast<uint4*>(a0 + 2 * A_WORD) = L;
-#ifdef SAT_TC_TRACE
-    if (threadIdx.x == 0) TC_TRACE(1, 201);
-#endif
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core
-#ifdef SAT_TC_TRACE
-    if (threadIdx.x == 0) TC_TRACE(1, 202);
-#endif
 }
 // the fp32 observation actually fed to the network, written AFTER the operand hand-off: the proxy fence in produce_x is a
 // MEMBAR that would otherwise wait for these global stores
@@ -415,7 +402,6 @@ actor_tc_kernel(const __grid_constant__ TcNet net0, const __grid_constant__ TcNe
                 const bool live_n = gn < n;
                 if (qa >= NSA) mbar_wait(&a_empty[sa], aphase ^ 1);
                 if (tid == 0) TC_TRACE(1, t * 16 + 15);
-                if (tid == 0) TC_TRACE(1, 203);
                 float xv[UPT];
                 produce_x(sm + OFF_A + sa * A_STAGE, a_off, part, live_n ? gn : n - 1, live_n, obs_f32, st, obs_stats, xv);
                 warp_arrive(&a_full[sa]);

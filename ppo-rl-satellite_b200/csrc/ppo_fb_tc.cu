@@ -364,13 +364,6 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                     if (heads > 1) { p1 = __ffma2_rn(h2, make_float2(wa.y, wb.y), p1); p2 = __ffma2_rn(h2, make_float2(wa.z, wb.z), p2); }
                 }
                 red[part * TM + r] = make_float4(p0.x + p0.y, p1.x + p1.y, p2.x + p2.y, 0.0f);
-#ifdef SAT_FB_DEBUG_H2
-                xs[row * XS_LD + 24 + part] = p0.x + p0.y;
-                if (row < HID) xs[row * XS_LD + 28 + part] = w3t[row].x;       // (every quarter writes the same value)
-#pragma unroll
-                for (int j4 = 0; j4 < CPT / 4; ++j4)
-                    *reinterpret_cast<float4*>(dz1g + row * HID + part * CPT + j4 * 4) = make_float4(va[j4 * 4], va[j4 * 4 + 1], va[j4 * 4 + 2], va[j4 * 4 + 3]);
-#endif
             }
             asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
             FB_TRACE(t * 16 + 5);
@@ -382,9 +375,6 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
                     const float* q = reinterpret_cast<const float*>(red) + k;
                     pre[k] = ((q[(0 * TM + r) * 4] + q[(1 * TM + r) * 4]) + q[(2 * TM + r) * 4]) + q[(3 * TM + r) * 4];
                 }
-#ifdef SAT_FB_DEBUG_H2
-                xs[row * XS_LD + 20] = pre[0]; xs[row * XS_LD + 21] = pre[1]; xs[row * XS_LD + 22] = pre[2];
-#endif
                 float d3[3] = {0.0f, 0.0f, 0.0f}, dls[3] = {0.0f, 0.0f, 0.0f}, loss = 0.0f;
                 if (live) {
                     if (CRITIC) {
@@ -491,13 +481,11 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
             tmem_sum64(lane_base, part * CPT, va);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             warp_arrive(acc_free);
-#ifndef SAT_FB_DEBUG_H2
             {
                 auto seg = [&](int b, int pc) { return part * CPT + b * 16 + pc * 4; };
                 scale_by_act_grad<TANH>(h1g + wrow0 * HID, HID, va, st, lane, seg);
                 store_rows(dz1g + wrow0 * HID, HID, va, st, lane, seg);
             }
-#endif
             FB_TRACE(t * 16 + 12);
         }
     }

@@ -42,28 +42,6 @@ for name, net in (("actor", na), ("critic", nc)):
     for nm, o, c in offs:
         a, b = out[0][name]["grads"][o:o + c], out[1][name]["grads"][o:o + c]
         print(f"  grad {nm:4s}: max |ffma| {a.abs().max().item():.3e}  max diff {(a - b).abs().max().item():.3e}")
-if os.environ.get("SAT_FB_DEBUG_H2") == "1":
-    # library built with SAT_NVCC_DEFINES=SAT_FB_DEBUG_H2: the tensor-core kernel leaves h2 in the dz1 buffer
-    for name, net, mod in (("actor", na, fused.actor), ("critic", nc, fused.critic)):
-        h1 = out[1][name]["h1"].view(mp, 256)[:mb].double()
-        h2 = out[1][name]["dz1"].view(mp, 256)[:mb].double()
-        W2, b2 = mod.fc2.weight.detach().double(), mod.fc2.bias.detach().double()
-        ref = h1 @ W2.T + b2
-        ref = torch.tanh(ref) if use_tanh else torch.relu(ref)
-        d = (h2 - ref).abs()
-        print(name, "h2 max diff", d.max().item(), "rows with diff > 1e-4:", int((d.max(1).values > 1e-4).sum()), "cols:", int((d.max(0).values > 1e-4).sum()))
-        W3 = (mod.mean_layer.weight if name == "actor" else mod.fc3.weight).detach().double()
-        pre_ref = h2 @ W3.T
-        pre_tc = out[1][name]["xs"].view(mp, 32)[:mb, 20:20 + W3.shape[0]].double()
-        dp = (pre_tc - pre_ref).abs()
-        print(name, "head pre-activation max diff", dp.max().item(), "rows off by > 1e-4:", int((dp.max(1).values > 1e-4).sum()), "first:", (dp.max(1).values > 1e-4).nonzero()[:12].flatten().tolist())
-        xs_tc = out[1][name]["xs"].view(mp, 32)
-        for q in range(4):
-            ref_q = h2[:, 64 * q:64 * q + 64] @ W3[0, 64 * q:64 * q + 64]
-            print("   quarter", q, "partial max diff", (xs_tc[:mb, 24 + q].double() - ref_q).abs().max().item())
-        print("   w3t.x vs W3[0]: max diff", (xs_tc[:256, 28].double() - W3[0]).abs().max().item(), " W3[0][:4]", W3[0][:4].tolist(), "w3t", xs_tc[:4, 28].tolist())
-        bad = (d > 1e-4).nonzero()
-        print("  first bad entries:", bad[:10].tolist())
 for name, net in (("actor", na), ("critic", nc)):
     heads = 3 if name == "actor" else 1
     o = 256 * 18 + 512 + 65536 + heads * 256

@@ -35,4 +35,3 @@ names = ["pre-l1_full", "l1_full", "R done"] + [f"chunk{k} arrived" for k in ran
 print("compute thread 0:")
 for tile in range(4):
     print("  tile", tile, " ".join(f"{names[j]}={cmp_[tile*16+j]:.2f}" for j in range(15)), f"X stage free={cmp_[tile*16+15]:.2f}")
-print("last X production: stage free %.2f, values ready %.2f, stored %.2f, fenced %.2f" % (cmp_[203], cmp_[200], cmp_[201], cmp_[202]))
