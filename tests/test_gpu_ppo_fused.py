@@ -290,3 +290,33 @@ def test_two_gpus_nccl_peer_memory_gradient_exchange():
     agent.optimize(s, act, logp, adv, vt, mini_batch_size=1024, fused=True)
     one = torch.cat([p.detach().reshape(-1) for p in list(agent.actor.parameters()) + list(agent.critic.parameters())]).cpu().numpy()
     assert np.abs(res[0][0] - one).max() <= 3e-5
+
+
+@pytest.mark.timeout(300)
+def test_tensor_core_and_ffma2_paths_agree_on_a_multi_tile_minibatch():
+    """the persistent tensor-core kernels with several row tiles per CTA (148 x 128 x 2 + 37 rows: three tiles on some CTAs, a
+    ragged last tile; dW2 slabs of unequal length) against the fp32 FFMA2 kernels on the same minibatch"""
+    from ppo_rl_satellite_b200 import _lib as L
+    lib = L.load()
+    mb = 148 * 128 * 2 + 37
+    args = _args(use_tanh=1, mb=mb, B=mb + 500)
+    fused, eager = _pair(args)
+    s, act, logp, adv, vt = _data(eager, mb + 500)
+    index = torch.randperm(mb + 500, device="cuda")[:mb].contiguous()
+    f = fused._fused_for(mb)
+    na, nc = f["nets"]
+    prev = lib.sat_ppo_use_tensor_cores(-1)
+    got = {}
+    try:
+        for tc in (0, 1):
+            lib.sat_ppo_use_tensor_cores(tc)
+            na.actor_grad(s, act, logp, adv.reshape(-1), index.data_ptr(), mb, 0.1, 0.01)
+            nc.critic_grad(s, vt.reshape(-1), index.data_ptr(), mb)
+            torch.cuda.synchronize()
+            got[tc] = (na.grads.clone(), nc.grads.clone())
+    finally:
+        lib.sat_ppo_use_tensor_cores(prev)
+    for a, b in zip(got[0], got[1]):
+        scale = a.abs().max().item()
+        assert scale > 0
+        assert (a - b).abs().max().item() <= 2e-6 * scale + 1e-9
