@@ -358,7 +358,7 @@ ppo_fb_tc_kernel(const float* __restrict__ packed, const unsigned char* __restri
 #pragma unroll
                 for (int j = 0; j < CPT; j += 2) {
                     const float4 wa = w3t[part * CPT + j], wb = w3t[part * CPT + j + 1];
-                    const float2 h2 = act2_scaled_fma<TANH>(__ffma2_rn(make_float2(va[j], va[j + 1]), make_float2(sc, sc), make_float2(wa.w, wb.w)));
+                    const float2 h2 = act2_scaled<TANH>(__ffma2_rn(make_float2(va[j], va[j + 1]), make_float2(sc, sc), make_float2(wa.w, wb.w)));
                     va[j] = h2.x; va[j + 1] = h2.y;
                     p0 = __ffma2_rn(h2, make_float2(wa.x, wb.x), p0);
                     if (heads > 1) { p1 = __ffma2_rn(h2, make_float2(wa.y, wb.y), p1); p2 = __ffma2_rn(h2, make_float2(wa.z, wb.z), p2); }
